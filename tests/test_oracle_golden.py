@@ -1,0 +1,78 @@
+"""CPU: pin oracle/rechorus_oracle.py against fixtures produced by the reference's own classes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rechorus_oracle as O
+from tests import golden_util as G
+
+ALL = [(m, f) for m, fs in G.MODEL_FIXTURES.items() for f in fs]
+
+
+@pytest.mark.parametrize("model,fixture", ALL)
+def test_oracle_matches_reference_fixture(model, fixture):
+    meta, w, batch, pred_ref, loss_ref, g_ref = G.load(fixture)
+    pred, loss, grads = O.loss_and_grads(model, w, batch, num_heads=meta.get("num_heads", 4))
+    # same ATen ops, possibly different association order -> fp32 rounding only
+    assert torch.allclose(pred, pred_ref, rtol=1e-5, atol=1e-6), (pred - pred_ref).abs().max()
+    assert abs(float(loss) - loss_ref) <= 1e-6
+    assert set(grads) == set(g_ref)
+    for k in g_ref:
+        assert torch.allclose(grads[k], g_ref[k], rtol=1e-4, atol=1e-6), (k, (grads[k] - g_ref[k]).abs().max())
+    # ranks are the integer output of the path (BaseRunner.py:63): must agree exactly on the fixture
+    assert np.array_equal(O.gt_rank(pred.numpy()), O.gt_rank(pred_ref.numpy()))
+
+
+@pytest.mark.parametrize("model,fixture", ALL)
+def test_oracle_fp64_replay_agrees(model, fixture):
+    """fp64 replay of the same weights: the fp32 reference output sits within 1e-5 of it (tie-breaker
+    for the north_star tolerance)."""
+    meta, w, batch, pred_ref, loss_ref, _ = G.load(fixture)
+    w64 = {k: v.double() for k, v in w.items()}
+    pred64 = O.scores(model, w64, batch, num_heads=meta.get("num_heads", 4))
+    assert (pred64 - pred_ref.double()).abs().max() < 1e-5
+    assert abs(float(O.bpr_loss(pred64)) - loss_ref) < 1e-5
+
+
+def test_loss_closed_form_gradient_matches_autograd():
+    g = torch.Generator().manual_seed(3)
+    for B, C in [(5, 2), (7, 10), (3, 100)]:
+        pred = (torch.randn(B, C, generator=g, dtype=torch.float64) * 2).requires_grad_(True)
+        loss = O.bpr_loss(pred)
+        loss.backward()
+        l2, g2 = O.bpr_loss_and_grad_fp64(pred.detach().numpy())
+        assert abs(float(loss) - l2) < 1e-12
+        assert np.abs(pred.grad.numpy() - g2).max() < 1e-12
+
+
+def test_loss_clamp_window_has_zero_gradient():
+    pred = np.zeros((2, 3))
+    pred[0] = [-50.0, 10.0, 10.0]      # S ~ e^-60 < 1e-8 -> clamped, zero gradient for that row
+    pred[1] = [0.3, 0.1, -0.2]
+    loss, g = O.bpr_loss_and_grad_fp64(pred)
+    assert np.all(g[0] == 0.0) and np.any(g[1] != 0.0)
+    t = torch.tensor(pred, requires_grad=True)
+    O.bpr_loss(t).backward()
+    assert np.abs(t.grad.numpy() - g).max() < 1e-12
+
+
+def test_runner_metrics_and_shuffle_fixture():
+    z = np.load(G.GOLDEN_DIR + "/runner_metrics.npz")
+    assert np.array_equal(O.gt_rank(z["pred"]), z["gt_rank"])
+    res = O.rank_metrics(z["pred"], [1, 5, 10, 50], ["HR", "NDCG"])
+    for k, v in res.items():
+        assert v == pytest.approx(float(z["m:" + k]), abs=1e-12)
+    torch.manual_seed(99)
+    item_id = torch.from_numpy(z["sh:item_id"])
+    shuffled, perm = O.shuffle_candidates(item_id)          # same CPU RNG stream as BaseRunner.py:189
+    assert np.array_equal(perm.numpy(), z["sh:indices"])
+    assert np.array_equal(shuffled.numpy(), z["sh:shuffled"])
+    restored = O.unshuffle_scores(torch.from_numpy(z["sh:scores"]), perm)
+    assert np.array_equal(restored.numpy(), z["sh:restored"])
+
+
+def test_negative_sampler_rejects_clicked_items():
+    rng = np.random.RandomState(0)
+    clicked = {u: set(range(1, 40)) for u in range(5)}
+    neg = O.sample_negatives([0, 1, 2, 3, 4] * 20, clicked, 50, 3, rng)
+    assert neg.min() >= 40 and neg.max() < 50
