@@ -1,0 +1,172 @@
+/* b200rec.h -- C ABI of libb200rec.so: the ReChorus training hot path as sm_100a CUDA kernels.
+ *
+ * The reference (THUwangcy/ReChorus) has no FFI: its hot path is Python calling ATen.  Each entry point below
+ * names the reference code it replaces (paths relative to the reference's src/).  The Python plugin layer
+ * (rechorus_b200/) binds these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (e.g. torch.Tensor.data_ptr()), row-major,
+ *     contiguous; tables/activations float32, ids int64 exactly as the reference's collate emits them
+ *     (models/BaseModel.py:135-152); row pointers must be 16-byte aligned and d % 4 == 0.
+ *   - all work is enqueued on `stream` (a cudaStream_t); no entry point synchronises or allocates.
+ *     Scratch memory is an explicit caller-provided workspace sized by the matching *_workspace_bytes().
+ *   - return value: 0 = ok; >0 = cudaError_t; <0 = B2R_E_* below.  b2r_last_error() gives the message
+ *     (thread-local).  Out-of-range ids never read out of bounds: they are clamped to row 0 and counted in
+ *     the device-side int32 `err_flag` the caller passes (may be NULL); the reference raises an ATen index
+ *     error in that case, the plugin raises IndexError when it polls the flag.
+ */
+#ifndef B200REC_H
+#define B200REC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_VERSION 100          /* major*10000 + minor*100 + patch */
+
+#define B2R_E_BADARG   (-1)      /* null pointer, d % 4 != 0, negative size ... */
+#define B2R_E_WORKSPACE (-2)     /* workspace too small */
+#define B2R_E_UNSUPPORTED (-3)   /* shape outside what the kernels were built for */
+
+typedef void* b2r_stream_t;      /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define B2R_API __attribute__((visibility("default")))
+#else
+#define B2R_API
+#endif
+
+B2R_API int         b2r_version(void);
+B2R_API const char* b2r_last_error(void);
+/* sm count / compute capability of the current device (148 / 10.0 on B200) */
+B2R_API int         b2r_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Measurement hooks for bench.py (no effect on results):
+ *  - b2r_launch_count(): kernels launched by this library so far (a CUB device-wide call counts as one);
+ *  - b2r_profile_arm(tag, ev_start, ev_stop): the next launch of the tagged kernel inside a whole-step entry
+ *    point is bracketed by cudaEventRecord on its own stream (one-shot; pass NULLs to disarm). */
+#define B2R_PROF_TAGS 8
+#define B2R_PROF_SCORE_FWD   0
+#define B2R_PROF_SCORE_BWDQ  1
+#define B2R_PROF_SEGMENT_I   2
+#define B2R_PROF_SEGMENT_U   3
+#define B2R_PROF_PLAN_I      4
+#define B2R_PROF_LOSS        5
+B2R_API long long b2r_launch_count(void);
+B2R_API int       b2r_profile_arm(int tag, void* ev_start, void* ev_stop);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scoring: pred[b,c] = < Q[qid[b]], T[ids[b,c]] >
+ * replaces  models/general/BPRMF.py:39-42  (embedding x2, mul, sum)  with Q=u_embeddings, qid=user_id
+ * and       models/sequential/SASRec.py:80-81                        with Q=user state [B,d], qid=NULL
+ * ids [B,C] int64, pred [B,C] float32.  n_q / n_t = number of rows in Q / T (for range checks).
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API int b2r_rowdot_fwd(const float* Q, const int64_t* qid, int64_t n_q,
+                   const float* T, const int64_t* ids, int64_t n_t,
+                   float* pred, int B, int C, int d, int32_t* err_flag, b2r_stream_t stream);
+
+/* Backward of the scoring w.r.t. the query side: dQ[b,:] = sum_c g[b,c] * T[ids[b,c],:]   (dense [B,d];
+ * replaces the mul/sum backward half of loss.backward(), helpers/BaseRunner.py:205).  Fixed summation
+ * order -> bit-reproducible. */
+B2R_API int b2r_rowdot_bwd_query(const float* g, const float* T, const int64_t* ids, int64_t n_t,
+                         float* dQ, int B, int C, int d, b2r_stream_t stream);
+
+/* Plain row gather out[r,:] = T[ids[r],:]  (nn.Embedding forward, e.g. NeuMF.py:63-66, SASRec.py:59) */
+B2R_API int b2r_gather_rows(const float* T, const int64_t* ids, int64_t n_t, float* out, int64_t n, int d,
+                    int32_t* err_flag, b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BPR loss + closed-form gradient (models/BaseModel.py:175-189; formula SURVEY.md A.4).
+ * pred [B,C] (column 0 = positive).  loss_out: 1 float.  grad_pred [B,C] = d loss / d pred (may be NULL).
+ * row_ws: B floats of scratch.  Deterministic (fixed-order reduction).
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API int b2r_bpr_loss(const float* pred, float* loss_out, float* grad_pred, float* row_ws,
+                 int B, int C, b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Index plan: the sorted, de-duplicated view of the ids a batch touches in one table.  It replaces the
+ * accumulation half of ATen's embedding_dense_backward (the autograd node behind nn.Embedding,
+ * BPRMF.py:31-32) and is what makes the scatter deterministic: every unique row gets ONE owner that sums
+ * its contributions in ascending position order.
+ *   in : ids[n] int64 in [0, n_rows)
+ *   out: sorted_key[n] uint32 (row ids ascending), sorted_pos[n] uint32 (original flat position, stable),
+ *        seg_start[n] int32 (index into sorted_* where unique row u starts), n_uniq (device int32)
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API size_t b2r_plan_workspace_bytes(int64_t n, int64_t n_rows);
+B2R_API int b2r_plan_build(const int64_t* ids, int64_t n, int64_t n_rows,
+                   uint32_t* sorted_key, uint32_t* sorted_pos, int32_t* seg_start, int32_t* n_uniq,
+                   void* ws, size_t ws_bytes, int32_t* err_flag, b2r_stream_t stream);
+
+/* One contribution stream into a table gradient: position p (0 <= p < n) contributes
+ *      coef[p] * src[row(p), :]      with   row(p) = src_id ? src_id[p / div] : p / div
+ * BPRMF item table : src = u_embeddings, coef = grad_pred, src_id = user_id, div = C     (dI = g * u)
+ * BPRMF user table : src = dQ [B,d],     coef = NULL(=1),  src_id = NULL,    div = 1
+ * NeuMF / SASRec   : src = dense gradient of the gathered activations, coef = NULL, div = 1            */
+typedef struct {
+    const float*   src;
+    const float*   coef;
+    const int64_t* src_id;
+    int64_t        n;
+    int32_t        div;
+    int32_t        _pad;
+} b2r_grad_source;
+
+/* Optimizer applied to the touched rows (helpers/BaseRunner.py:110-114 builds torch.optim.<name>;
+ * here the update is row-sparse / lazy: untouched rows do not move).  kind: 0 SGD, 1 Adam, 2 Adagrad.
+ * Coupled L2 (weight_decay) as torch.optim does: g += wd * w.  bc1/bc2 = 1 - beta^t for Adam. */
+typedef struct {
+    int32_t kind;
+    float   lr, beta1, beta2, eps, weight_decay, bc1, bc2;
+} b2r_optim;
+
+/* Segment reduce over a plan built on the concatenation of up to two sources' ids
+ * (positions [0, s0.n) belong to s0, [s0.n, s0.n + s1.n) to s1; s1 may be NULL).
+ *   mode 0: write row-sparse gradient: uniq_rows[u] (int64) and grad_rows[u,:]  (u < *n_uniq)
+ *   mode 1: add into a dense gradient table dense[row,:] += (one writer per row, no atomics)
+ *   mode 2: apply `opt` in place to W (and state m, v) for the touched rows -- fused backward+optimizer
+ * replaces embedding_dense_backward + grad zero-fill + the embedding part of optimizer.step()
+ * (helpers/BaseRunner.py:193,205,206). */
+B2R_API int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sorted_pos, const int32_t* seg_start,
+                      const int32_t* n_uniq, int64_t n, int d,
+                      const b2r_grad_source* s0, const b2r_grad_source* s1,
+                      int mode, int64_t* uniq_rows, float* grad_rows, float* dense,
+                      float* W, float* m, float* v, const b2r_optim* opt, b2r_stream_t stream);
+
+/* Fast, order-nondeterministic alternative to plan+segment for mode 1 (dense += via red.global.add.v4.f32) */
+B2R_API int b2r_scatter_add_atomic(const int64_t* ids, int64_t n_rows, const b2r_grad_source* s, int d,
+                           float* dense, int32_t* err_flag, b2r_stream_t stream);
+
+/* Dense optimizer step over a whole parameter tensor (exact torch.optim semantics; used for the small dense
+ * parameters of NeuMF/SASRec and for the exact-reference dense-Adam mode of the embedding tables). */
+B2R_API int b2r_dense_optim(float* W, const float* grad, float* m, float* v, int64_t numel,
+                    const b2r_optim* opt, b2r_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * One whole BPRMF training step enqueued from C (no Python between kernels):
+ *   gather u = U[uid] -> scores -> BPR loss + grad -> dQ -> row-sparse fused optimizer on I and on U.
+ * Replaces one iteration of the hot loop helpers/BaseRunner.py:193-206 for models/general/BPRMF.py (the
+ * per-row candidate shuffle of :187-191 is a mathematical no-op for this model and is not performed).
+ * The index plans are built on a library-owned side stream so the sort overlaps the gather kernels.
+ * Tables are updated in place with the lazy row-sparse rule documented at b2r_optim.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float*  U;  float* I;            /* [n_users, d], [n_items, d]                       */
+    float*  Um; float* Uv;           /* optimizer state for U (Adam: m, v; Adagrad: v)   */
+    float*  Im; float* Iv;           /* optimizer state for I                            */
+    int64_t n_users, n_items;
+    int32_t d, _pad;
+} b2r_bprmf_tables;
+
+B2R_API size_t b2r_bprmf_step_workspace_bytes(int B, int C, int d, int64_t n_users, int64_t n_items);
+B2R_API int b2r_bprmf_train_step(const b2r_bprmf_tables* t, const int64_t* uid, const int64_t* iid, int B, int C,
+                         const b2r_optim* opt, float* loss_out, void* ws, size_t ws_bytes,
+                         int32_t* err_flag, b2r_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REC_H */

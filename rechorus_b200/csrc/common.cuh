@@ -1,0 +1,108 @@
+// common.cuh -- shared device/host helpers for libb200rec.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/b200rec.h"
+
+#define B2R_FULL_MASK 0xffffffffu
+
+namespace b2r {
+
+// ---- thread-local error string -------------------------------------------------------------------
+char* err_buf();
+int   set_error(int code, const char* fmt, ...);
+
+#define B2R_REQUIRE(cond, code, ...)                        \
+    do {                                                    \
+        if (!(cond)) return b2r::set_error((code), __VA_ARGS__); \
+    } while (0)
+
+#define B2R_CUDA_OK(expr)                                                              \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess)                                                         \
+            return b2r::set_error((int)_e, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define B2R_LAUNCH_OK(name)                                                            \
+    do {                                                                               \
+        b2r::count_launch();                                                           \
+        cudaError_t _e = cudaGetLastError();                                           \
+        if (_e != cudaSuccess)                                                         \
+            return b2r::set_error((int)_e, "launch of %s failed: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
+
+// bookkeeping for bench.py: number of kernel launches issued by this library, and optional CUDA-event brackets
+// around one tagged kernel (armed per call with b2r_profile_arm, consumed by the next launch with that tag)
+void count_launch();
+void profile_begin(int tag, cudaStream_t s);
+void profile_end(int tag, cudaStream_t s);
+
+static inline cudaStream_t as_stream(b2r_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device helpers ---------------------------------------------------------------------------------
+
+// streaming 128-bit load of a table row chunk: read-only path, do not allocate in L1 (each row chunk is
+// used once per CTA; reuse across CTAs is served by the 126 MB L2)
+__device__ __forceinline__ float4 ld_row4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+// cached 128-bit load (small, re-used operands such as the query row or the user-row block)
+__device__ __forceinline__ float4 ld4(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+}
+
+__device__ __forceinline__ void st4(float* p, const float4& v) {
+    *reinterpret_cast<float4*>(p) = v;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float c, const float4& x) {
+    acc.x = fmaf(c, x.x, acc.x);
+    acc.y = fmaf(c, x.y, acc.y);
+    acc.z = fmaf(c, x.z, acc.z);
+    acc.w = fmaf(c, x.w, acc.w);
+}
+
+// butterfly sum over the LPR lanes (a power of two <= 32) that share one embedding row
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(B2R_FULL_MASK, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(B2R_FULL_MASK, v, o));
+    return v;
+}
+
+// id range check: clamp to row 0 and count the violation (reference: ATen index error)
+__device__ __forceinline__ int64_t checked_id(int64_t id, int64_t n_rows, int32_t* err_flag) {
+    if (id < 0 || id >= n_rows) {
+        if (err_flag) atomicAdd(err_flag, 1);
+        return 0;
+    }
+    return id;
+}
+
+}  // namespace b2r

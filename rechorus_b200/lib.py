@@ -1,0 +1,103 @@
+"""ctypes binding of libb200rec.so (the C ABI declared in include/b200rec.h).
+
+There is deliberately NO fallback: if the shared library is missing or an entry point fails, the caller
+gets an exception -- never a silent PyTorch/CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb200rec.so")
+
+c_i64p = C.c_void_p      # device pointers travel as integers
+c_f32p = C.c_void_p
+
+
+class GradSource(C.Structure):
+    """b2r_grad_source (include/b200rec.h)"""
+    _fields_ = [("src", C.c_void_p), ("coef", C.c_void_p), ("src_id", C.c_void_p),
+                ("n", C.c_int64), ("div", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Optim(C.Structure):
+    """b2r_optim (include/b200rec.h)"""
+    _fields_ = [("kind", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("weight_decay", C.c_float), ("bc1", C.c_float), ("bc2", C.c_float)]
+
+
+class BprmfTables(C.Structure):
+    """b2r_bprmf_tables (include/b200rec.h)"""
+    _fields_ = [("U", C.c_void_p), ("I", C.c_void_p), ("Um", C.c_void_p), ("Uv", C.c_void_p),
+                ("Im", C.c_void_p), ("Iv", C.c_void_p), ("n_users", C.c_int64), ("n_items", C.c_int64),
+                ("d", C.c_int32), ("_pad", C.c_int32)]
+
+
+OPT_SGD, OPT_ADAM, OPT_ADAGRAD = 0, 1, 2
+PROF_SCORE_FWD, PROF_SCORE_BWDQ, PROF_SEGMENT_I, PROF_SEGMENT_U, PROF_PLAN_I, PROF_LOSS = range(6)
+
+# name -> (restype, argtypes); must list every symbol include/b200rec.h declares (tests/test_abi.py checks)
+SIGNATURES = {
+    "b2r_version": (C.c_int, []),
+    "b2r_last_error": (C.c_char_p, []),
+    "b2r_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "b2r_launch_count": (C.c_longlong, []),
+    "b2r_profile_arm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "b2r_rowdot_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b2r_rowdot_bwd_query": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2r_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    "b2r_bpr_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b2r_plan_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "b2r_plan_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "b2r_segment_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                    C.POINTER(GradSource), C.POINTER(GradSource), C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(Optim), C.c_void_p]),
+    "b2r_scatter_add_atomic": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(GradSource), C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "b2r_dense_optim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.POINTER(Optim), C.c_void_p]),
+    "b2r_bprmf_step_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]),
+    "b2r_bprmf_train_step": (C.c_int, [C.POINTER(BprmfTables), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.POINTER(Optim), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                       C.c_void_p]),
+}
+
+
+class B200RecError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libb200rec.so (built in-tree by `python -m rechorus_b200.build`); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200RecError(
+            f"{LIB_PATH} not found: build it with `python -m rechorus_b200.build` "
+            "(there is no PyTorch/CPU fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.b2r_version()
+    if got // 100 != 1:
+        raise B200RecError(f"libb200rec.so ABI version {got} does not match this package (expects 1xx)")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().b2r_last_error().decode("utf-8", "replace")
+        raise B200RecError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,111 @@
+"""Optimizer for the ``model.optimizer`` seam of the reference's runner (helpers/BaseRunner.py:176-177,193,206).
+
+``BaseRunner.fit`` only builds ``torch.optim.<name>`` when ``model.optimizer is None``; an object with
+``zero_grad()`` / ``step()`` placed there beforehand is used as-is.  ``RowSparseOptimizer`` is that object:
+
+* embedding tables in 'fused' mode (rechorus_b200.ops.set_table_mode): the contribution streams parked by the
+  backward pass are reduced per unique row and the SGD/Adam/Adagrad update is applied in the same kernel
+  (b2r_segment_apply mode 2).  The update is *row-sparse / lazy*: rows the batch did not touch do not move.
+  This is NOT what the reference's dense ``torch.optim.Adam`` does (there the moments keep moving untouched
+  rows and L2 decays them every step); it is the semantics of ``torch.optim.SparseAdam`` and of production
+  recommender training.  Keep tables in 'dense' mode to reproduce the reference exactly.
+* every other parameter (and tables left in 'dense' mode) gets the exact dense torch.optim formula
+  (b2r_dense_optim), with the reference's two parameter groups: names containing 'bias' have weight_decay 0
+  (models/BaseModel.py:64-73).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import lib as _lib
+from . import ops
+
+_KIND = {"SGD": _lib.OPT_SGD, "Adam": _lib.OPT_ADAM, "Adagrad": _lib.OPT_ADAGRAD}
+_DEFAULT_EPS = {"SGD": 0.0, "Adam": 1e-8, "Adagrad": 1e-10}
+
+
+class RowSparseOptimizer:
+    def __init__(self, model: torch.nn.Module, name: str = "Adam", lr: float = 1e-3, l2: float = 0.0,
+                 betas=(0.9, 0.999), eps: float | None = None):
+        if name not in _KIND:
+            raise ValueError(f"optimizer {name!r} not supported by the fused path (have {sorted(_KIND)})")
+        self.name, self.kind = name, _KIND[name]
+        self.lr, self.l2, self.betas = float(lr), float(l2), (float(betas[0]), float(betas[1]))
+        self.eps = _DEFAULT_EPS[name] if eps is None else float(eps)
+        self.t = 0
+        self.model = model
+        self._entries: List[dict] = []
+        for pname, p in model.named_parameters():
+            if not p.requires_grad:
+                continue
+            wd = 0.0 if "bias" in pname else self.l2
+            e = {"name": pname, "p": p, "wd": wd, "m": None, "v": None}
+            if self.kind == _lib.OPT_ADAM:
+                e["m"] = torch.zeros_like(p.data)
+            if self.kind != _lib.OPT_SGD:
+                e["v"] = torch.zeros_like(p.data)
+            self._entries.append(e)
+
+    # -- torch.optim-like surface used by BaseRunner.fit ------------------------------------------------
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        for e in self._entries:
+            p = e["p"]
+            p.grad = None
+            pend = getattr(p, "_b2r_pending", None)
+            if pend:
+                pend.clear()
+
+    def _opt(self, wd: float) -> _lib.Optim:
+        b1, b2 = self.betas
+        return _lib.Optim(self.kind, self.lr, b1, b2, self.eps, wd, 1.0 - b1 ** self.t, 1.0 - b2 ** self.t)
+
+    @torch.no_grad()
+    def step(self) -> None:
+        self.t += 1
+        for e in self._entries:
+            p = e["p"]
+            pend = getattr(p, "_b2r_pending", None)
+            if ops.table_mode(p) == "fused" and pend is not None:
+                if not pend:
+                    continue
+                if len(pend) > 2:
+                    raise _lib.B200RecError(f"{e['name']}: more than two gradient streams into one table")
+                ids = pend[0][0] if len(pend) == 1 else torch.cat([pend[0][0], pend[1][0]])
+                plan = ops.IndexPlan(ids, p.shape[0])
+                plan.apply_optimizer(p.data, e["m"], e["v"], self._opt(e["wd"]), [s for _, s in pend])
+                pend.clear()
+            elif p.grad is not None:
+                if p.grad.is_sparse:
+                    raise _lib.B200RecError(f"{e['name']}: sparse .grad -- use table mode 'fused' or 'dense' "
+                                            "with RowSparseOptimizer, or torch.optim.SparseAdam")
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                ops.dense_optim(p.data, g, e["m"], e["v"], self._opt(e["wd"]))
+
+    def entry(self, param: torch.Tensor) -> dict:
+        """state record (m, v, weight decay) of one parameter -- used by the models' C-side fused step"""
+        for e in self._entries:
+            if e["p"] is param:
+                return e
+        raise KeyError("parameter is not managed by this optimizer")
+
+    def advance(self) -> int:
+        """count one optimizer step taken outside ``step()`` (the C-side whole-step entry points)"""
+        self.t += 1
+        return self.t
+
+    # -- checkpointing (the reference saves no optimizer state; kept for completeness) -------------------
+    def state_dict(self) -> Dict:
+        return {"t": self.t, "name": self.name,
+                "state": {e["name"]: {"m": e["m"], "v": e["v"]} for e in self._entries}}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        self.t = int(sd["t"])
+        for e in self._entries:
+            st = sd["state"].get(e["name"])
+            if st is None:
+                continue
+            for k in ("m", "v"):
+                if e[k] is not None and st[k] is not None:
+                    e[k].copy_(st[k])

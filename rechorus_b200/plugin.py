@@ -1,0 +1,304 @@
+"""The reference's model plugin contract, re-hosted on the sm_100a kernels.
+
+ReChorus discovers a model class by name and drives it through a fixed surface:
+``parse_model_args`` / ``__init__(args, corpus)`` / ``forward(feed_dict) -> {'prediction': [B, C]}`` /
+``loss(out_dict)`` / ``customize_parameters`` / ``save_model`` / ``load_model`` / inner ``Dataset``.
+This module provides that surface twice:
+
+* stand-alone classes (``BPRMF``, ``NeuMF``, ``SASRec``) usable without the reference checkout -- this is what
+  the tests, ``bench.py`` and ``rechorus_b200.runner.BaseRunner`` use (the GPU box has no /root/reference);
+* kernel *mixins* (``BPRMFKernels`` ...) that ``rechorus_b200.overlay`` grafts onto the reference's own
+  ``GeneralModel`` / ``SequentialModel`` so the reference's unchanged ``src/main.py`` runs them.
+
+State-dict keys and shapes equal the reference's so ``.pt`` checkpoints interchange.
+There is no CPU path: calling ``forward`` with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Dict, List
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.utils.rnn import pad_sequence
+from torch.utils.data import Dataset as TorchDataset
+
+from . import ops
+
+# ======================================================================================================
+# kernel mixins: parameters + forward/loss/inference, independent of which GeneralModel base hosts them
+# ======================================================================================================
+
+
+class _KernelModelMixin:
+    """Shared by every kernel-backed model: table registry + loss + optional inference hook."""
+
+    def _register_tables(self, *params: nn.Parameter, mode: str = "dense") -> None:
+        self._b2r_tables: List[nn.Parameter] = list(params)
+        for p in params:
+            ops.set_table_mode(p, mode)
+
+    def sparse_tables(self) -> List[nn.Parameter]:
+        return list(getattr(self, "_b2r_tables", []))
+
+    def set_table_mode(self, mode: str) -> None:
+        """'dense' (exact reference semantics with stock torch.optim), 'sparse' (torch sparse grads) or
+        'fused' (row-sparse fused optimizer, rechorus_b200.optim.RowSparseOptimizer)."""
+        for p in self.sparse_tables():
+            ops.set_table_mode(p, mode)
+
+    # models/BaseModel.py:175-189
+    def loss(self, out_dict: dict) -> torch.Tensor:
+        return ops.bpr_loss(out_dict["prediction"])
+
+    # helpers/BaseRunner.py:237 looks for this optional hook: scoring without building an autograd graph
+    def inference(self, feed_dict: dict) -> dict:
+        with torch.no_grad():
+            return self.forward(feed_dict)
+
+
+class BPRMFKernels(_KernelModelMixin):
+    """models/general/BPRMF.py:18-45 (BPRMFBase) on K1/K2."""
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument("--emb_size", type=int, default=64, help="Size of embedding vectors.")
+        parser.add_argument("--table_mode", type=str, default="dense",
+                            help="embedding gradient form: dense | sparse | fused (see rechorus_b200.ops)")
+        return parser
+
+    def _base_init(self, args, corpus):
+        self.emb_size = args.emb_size
+        if self.emb_size % 4 != 0:
+            raise ValueError("rechorus_b200 kernels need emb_size % 4 == 0")
+        self._base_define_params()
+        self.apply(self.init_weights)
+        self._register_tables(self.u_embeddings.weight, self.i_embeddings.weight,
+                              mode=getattr(args, "table_mode", "dense"))
+
+    def _base_define_params(self):
+        # same module/parameter names as BPRMF.py:31-32 -> identical state_dict keys
+        self.u_embeddings = nn.Embedding(self.user_num, self.emb_size)
+        self.i_embeddings = nn.Embedding(self.item_num, self.emb_size)
+
+    def forward(self, feed_dict):
+        self.check_list = []
+        u_ids = feed_dict["user_id"]        # [B]
+        i_ids = feed_dict["item_id"]        # [B, C]
+        u = ops.embedding(self.u_embeddings.weight, u_ids)            # [B, d]   (gather kernel)
+        pred = ops.score(u, self.i_embeddings.weight, i_ids)          # [B, C]   (gather + dot kernel)
+        return {"prediction": pred.view(feed_dict["batch_size"], -1)}
+
+    def train_step(self, feed_dict) -> torch.Tensor:
+        """One whole training step (forward, BPR loss, backward, row-sparse optimizer update) enqueued by a
+        single C call (b2r_bprmf_train_step) -- the body of helpers/BaseRunner.py:193-206 for this model.
+        Needs ``self.optimizer`` to be a ``RowSparseOptimizer``.  Returns the loss as a device scalar."""
+        return ops.bprmf_train_step(self.u_embeddings.weight, self.i_embeddings.weight, self.optimizer,
+                                    feed_dict["user_id"], feed_dict["item_id"])
+
+
+# ======================================================================================================
+# stand-alone hosts mirroring models/BaseModel.py (used when the reference checkout is absent)
+# ======================================================================================================
+
+
+class BaseModel(nn.Module):
+    """API mirror of models/BaseModel.py:16-152."""
+    reader, runner = None, None
+    extra_log_args: List[str] = []
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument("--model_path", type=str, default="", help="Model save path.")
+        parser.add_argument("--buffer", type=int, default=1, help="Whether to buffer feed dicts for dev/test")
+        return parser
+
+    @staticmethod
+    def init_weights(m):
+        # BaseModel.py:29-35: N(0, 0.01) for Linear weight AND bias and for Embedding; LayerNorm untouched
+        if isinstance(m, nn.Linear):
+            nn.init.normal_(m.weight, mean=0.0, std=0.01)
+            if m.bias is not None:
+                nn.init.normal_(m.bias, mean=0.0, std=0.01)
+        elif isinstance(m, nn.Embedding):
+            nn.init.normal_(m.weight, mean=0.0, std=0.01)
+
+    def __init__(self, args, corpus):
+        super().__init__()
+        self.device = args.device
+        self.model_path = args.model_path
+        self.buffer = args.buffer
+        self.optimizer = None
+        self.check_list = []
+
+    def forward(self, feed_dict: dict) -> dict:
+        raise NotImplementedError
+
+    def loss(self, out_dict: dict) -> torch.Tensor:
+        raise NotImplementedError
+
+    def customize_parameters(self) -> list:
+        # BaseModel.py:64-73: parameters whose name contains 'bias' get weight_decay 0
+        weight_p, bias_p = [], []
+        for name, p in self.named_parameters():
+            if p.requires_grad:
+                (bias_p if "bias" in name else weight_p).append(p)
+        return [{"params": weight_p}, {"params": bias_p, "weight_decay": 0}]
+
+    def save_model(self, model_path=None):
+        model_path = model_path or self.model_path
+        d = os.path.dirname(model_path)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        torch.save(self.state_dict(), model_path)
+
+    def load_model(self, model_path=None):
+        model_path = model_path or self.model_path
+        self.load_state_dict(torch.load(model_path, map_location=self.device))
+        logging.info("Load model from " + model_path)
+
+    def count_variables(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def actions_after_train(self):
+        pass
+
+    class Dataset(TorchDataset):
+        """BaseModel.py:98-152: per-phase view of the corpus that yields feed dicts and collates them."""
+
+        def __init__(self, model, corpus, phase: str):
+            self.model, self.corpus, self.phase = model, corpus, phase
+            self.buffer_dict = {}
+            self.data = corpus.data_df[phase].to_dict("list")
+
+        def __len__(self):
+            for key in self.data:
+                return len(self.data[key])
+            return 0
+
+        def __getitem__(self, index: int) -> dict:
+            if self.model.buffer and self.phase != "train":
+                return self.buffer_dict[index]
+            return self._get_feed_dict(index)
+
+        def _get_feed_dict(self, index: int) -> dict:
+            raise NotImplementedError
+
+        def prepare(self):
+            if self.model.buffer and self.phase != "train":
+                for i in range(len(self)):
+                    self.buffer_dict[i] = self._get_feed_dict(i)
+
+        def actions_before_epoch(self):
+            pass
+
+        def collate_batch(self, feed_dicts: List[dict]) -> dict:
+            # BaseModel.py:135-152: stack equal-length arrays; right-pad ragged ones (histories) with 0
+            out = {}
+            for key in feed_dicts[0]:
+                vals = [d[key] for d in feed_dicts]
+                ragged = isinstance(vals[0], np.ndarray) and any(len(v) != len(vals[0]) for v in vals)
+                if ragged:
+                    out[key] = pad_sequence([torch.from_numpy(np.asarray(v)) for v in vals], batch_first=True)
+                else:
+                    out[key] = torch.from_numpy(np.array(vals))
+            out["batch_size"] = len(feed_dicts)
+            out["phase"] = self.phase
+            return out
+
+
+class GeneralModel(BaseModel):
+    """API mirror of models/BaseModel.py:154-214."""
+    reader, runner = "BaseReader", "BaseRunner"
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument("--num_neg", type=int, default=1, help="The number of negative items during training.")
+        parser.add_argument("--dropout", type=float, default=0, help="Dropout probability for each deep layer")
+        parser.add_argument("--test_all", type=int, default=0, help="Whether testing on all the items.")
+        return BaseModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        super().__init__(args, corpus)
+        self.user_num = corpus.n_users
+        self.item_num = corpus.n_items
+        self.num_neg = args.num_neg
+        self.dropout = args.dropout
+        self.test_all = args.test_all
+
+    class Dataset(BaseModel.Dataset):
+        def _get_feed_dict(self, index):
+            # BaseModel.py:192-203: column 0 = target, then the negatives (all items when test_all)
+            target = self.data["item_id"][index]
+            if self.phase != "train" and self.model.test_all:
+                negs = np.arange(1, self.corpus.n_items)
+            else:
+                negs = self.data["neg_items"][index]
+            return {"user_id": self.data["user_id"][index],
+                    "item_id": np.concatenate([[target], negs]).astype(int)}
+
+        def actions_before_epoch(self):
+            # BaseModel.py:206-214: uniform negatives from NumPy's global RNG, rejected against train clicks
+            n = len(self)
+            neg = np.random.randint(1, self.corpus.n_items, size=(n, self.model.num_neg))
+            clicked = self.corpus.train_clicked_set
+            for i, u in enumerate(self.data["user_id"]):
+                seen = clicked[u]
+                for j in range(self.model.num_neg):
+                    while neg[i][j] in seen:
+                        neg[i][j] = np.random.randint(1, self.corpus.n_items)
+            self.data["neg_items"] = neg
+
+
+class SequentialModel(GeneralModel):
+    """API mirror of models/BaseModel.py:216-245."""
+    reader = "SeqReader"
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument("--history_max", type=int, default=20, help="Maximum length of history.")
+        return GeneralModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        super().__init__(args, corpus)
+        self.history_max = args.history_max
+
+    class Dataset(GeneralModel.Dataset):
+        def __init__(self, model, corpus, phase):
+            super().__init__(model, corpus, phase)
+            keep = np.array(self.data["position"]) > 0          # history length must be non-zero
+            for key in self.data:
+                self.data[key] = np.array(self.data[key], dtype=object)[keep].tolist()
+
+        def _get_feed_dict(self, index):
+            fd = super()._get_feed_dict(index)
+            pos = self.data["position"][index]
+            seq = self.corpus.user_his[fd["user_id"]][:pos]
+            if self.model.history_max > 0:
+                seq = seq[-self.model.history_max:]
+            fd["history_items"] = np.array([x[0] for x in seq])
+            fd["history_times"] = np.array([x[1] for x in seq])
+            fd["lengths"] = len(fd["history_items"])
+            return fd
+
+
+# ======================================================================================================
+# concrete stand-alone models
+# ======================================================================================================
+
+
+class BPRMF(BPRMFKernels, GeneralModel):
+    """Drop-in for models/general/BPRMF.py:47-63."""
+    reader, runner = "BaseReader", "BaseRunner"
+    extra_log_args = ["emb_size", "batch_size"]
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser = BPRMFKernels.parse_model_args(parser)
+        return GeneralModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        GeneralModel.__init__(self, args, corpus)
+        self._base_init(args, corpus)

@@ -1,0 +1,217 @@
+"""Stand-alone mirror of the reference's runner surface (helpers/BaseRunner.py) for use without the
+reference checkout: same flags, same ``train / fit / evaluate / predict / evaluate_method / print_res``
+semantics, same CPU RNG stream for the per-batch candidate shuffle.  Additions (all opt-in flags):
+``--fused_optimizer 1`` installs ``RowSparseOptimizer`` through the ``model.optimizer`` seam
+(BaseRunner.py:176-177) and switches the embedding tables to 'fused' gradient mode.
+"""
+from __future__ import annotations
+
+import gc
+import logging
+import os
+from time import time
+from typing import Dict, List
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+from .optim import RowSparseOptimizer
+
+
+def batch_to_device(batch: dict, device) -> dict:
+    # utils/utils.py:30-34
+    for k, v in batch.items():
+        if isinstance(v, torch.Tensor):
+            batch[k] = v.to(device)
+    return batch
+
+
+def format_metric(result: Dict[str, float]) -> str:
+    # utils/utils.py:54-69: "HR@5:0.1234,NDCG@5:0.0567" sorted by k then metric name
+    keys = sorted(result, key=lambda s: (int(s.split("@")[1]) if "@" in s else 0, s.split("@")[0]))
+    parts = []
+    for k in keys:
+        v = result[k]
+        parts.append(f"{k}:{v:<.4f}" if isinstance(v, (float, np.floating)) else f"{k}:{v}")
+    return ",".join(parts)
+
+
+class BaseRunner:
+    @staticmethod
+    def parse_runner_args(parser):
+        # helpers/BaseRunner.py:20-49 (same names, defaults and help strings' meaning)
+        parser.add_argument("--epoch", type=int, default=200, help="Number of epochs.")
+        parser.add_argument("--check_epoch", type=int, default=1, help="Check some tensors every check_epoch.")
+        parser.add_argument("--test_epoch", type=int, default=-1, help="Print test results every test_epoch (-1: never).")
+        parser.add_argument("--early_stop", type=int, default=10, help="Epochs of continuous dev drop before stopping.")
+        parser.add_argument("--lr", type=float, default=1e-3, help="Learning rate.")
+        parser.add_argument("--l2", type=float, default=0, help="Weight decay in optimizer.")
+        parser.add_argument("--batch_size", type=int, default=256, help="Batch size during training.")
+        parser.add_argument("--eval_batch_size", type=int, default=256, help="Batch size during testing.")
+        parser.add_argument("--optimizer", type=str, default="Adam", help="optimizer: SGD, Adam, Adagrad, Adadelta")
+        parser.add_argument("--num_workers", type=int, default=5, help="DataLoader worker processes.")
+        parser.add_argument("--pin_memory", type=int, default=0, help="pin_memory in DataLoader")
+        parser.add_argument("--topk", type=str, default="5,10,20,50", help="Cut-offs of the ranking metrics.")
+        parser.add_argument("--metric", type=str, default="NDCG,HR", help="metrics: NDCG, HR")
+        parser.add_argument("--main_metric", type=str, default="", help="Metric that selects the best model.")
+        parser.add_argument("--fused_optimizer", type=int, default=0,
+                            help="1: row-sparse fused SGD/Adam/Adagrad (rechorus_b200.optim) instead of torch.optim")
+        return parser
+
+    @staticmethod
+    def evaluate_method(predictions: np.ndarray, topk: list, metrics: list) -> Dict[str, float]:
+        """helpers/BaseRunner.py:52-78.  Column 0 holds the ground-truth item's score; its rank is the number
+        of candidates scoring >= it (ties count against it)."""
+        gt_rank = (predictions >= predictions[:, 0].reshape(-1, 1)).sum(axis=-1)
+        out = {}
+        for k in topk:
+            hit = gt_rank <= k
+            for metric in metrics:
+                key = f"{metric}@{k}"
+                if metric == "HR":
+                    out[key] = hit.mean()
+                elif metric == "NDCG":
+                    out[key] = (hit / np.log2(gt_rank + 1)).mean()
+                else:
+                    raise ValueError(f"Undefined evaluation metric: {metric}.")
+        return out
+
+    def __init__(self, args):
+        self.train_models = getattr(args, "train", 1)
+        self.epoch = args.epoch
+        self.check_epoch = args.check_epoch
+        self.test_epoch = args.test_epoch
+        self.early_stop = args.early_stop
+        self.learning_rate = args.lr
+        self.batch_size = args.batch_size
+        self.eval_batch_size = args.eval_batch_size
+        self.l2 = args.l2
+        self.optimizer_name = args.optimizer
+        self.num_workers = args.num_workers
+        self.pin_memory = args.pin_memory
+        self.fused_optimizer = getattr(args, "fused_optimizer", 0)
+        self.topk = [int(x) for x in args.topk.split(",")]
+        self.metrics = [m.strip().upper() for m in args.metric.split(",")]
+        self.main_metric = args.main_metric or f"{self.metrics[0]}@{self.topk[0]}"
+        self.main_topk = int(self.main_metric.split("@")[1]) if "@" in self.main_metric else 0
+        self.time = None
+        log_file = getattr(args, "log_file", "") or ""
+        self.log_path = os.path.dirname(log_file)
+        self.save_appendix = log_file.split("/")[-1].split(".")[0]
+
+    def _check_time(self, start=False):
+        if self.time is None or start:
+            self.time = [time()] * 2
+            return self.time[0]
+        prev = self.time[1]
+        self.time[1] = time()
+        return self.time[1] - prev
+
+    def _build_optimizer(self, model):
+        logging.info("Optimizer: " + self.optimizer_name)
+        if self.fused_optimizer:
+            model.set_table_mode("fused")
+            return RowSparseOptimizer(model, self.optimizer_name, lr=self.learning_rate, l2=self.l2)
+        cls = getattr(torch.optim, self.optimizer_name)       # helpers/BaseRunner.py:112
+        return cls(model.customize_parameters(), lr=self.learning_rate, weight_decay=self.l2)
+
+    # ---------------------------------------------------------------------------------------------
+    def train(self, data_dict):
+        model = data_dict["train"].model
+        main_results, dev_results = [], []
+        self._check_time(start=True)
+        try:
+            for epoch in range(self.epoch):
+                self._check_time()
+                gc.collect()
+                loss = self.fit(data_dict["train"], epoch=epoch + 1)
+                if np.isnan(loss):
+                    logging.info("Loss is Nan. Stop training at %d." % (epoch + 1))
+                    break
+                train_t = self._check_time()
+                dev = self.evaluate(data_dict["dev"], [self.main_topk], self.metrics)
+                dev_results.append(dev)
+                main_results.append(dev[self.main_metric])
+                line = "Epoch {:<5} loss={:<.4f} [{:<3.1f} s]	dev=({})".format(epoch + 1, loss, train_t,
+                                                                               format_metric(dev))
+                if self.test_epoch > 0 and epoch % self.test_epoch == 0:
+                    test = self.evaluate(data_dict["test"], self.topk[:1], self.metrics)
+                    line += " test=({})".format(format_metric(test))
+                line += " [{:<.1f} s]".format(self._check_time())
+                if max(main_results) == main_results[-1] or (hasattr(model, "stage") and model.stage == 1):
+                    model.save_model()
+                    line += " *"
+                logging.info(line)
+                if self.early_stop > 0 and self.eval_termination(main_results):
+                    logging.info("Early stop at %d based on dev result." % (epoch + 1))
+                    break
+        except KeyboardInterrupt:
+            logging.info("Early stop manually")
+        best = main_results.index(max(main_results))
+        logging.info(os.linesep + "Best Iter(dev)={:>5}\t dev=({}) [{:<.1f} s] ".format(
+            best + 1, format_metric(dev_results[best]), self.time[1] - self.time[0]))
+        model.load_model()
+
+    def fit(self, dataset, epoch=-1) -> float:
+        """helpers/BaseRunner.py:174-208, step for step."""
+        model = dataset.model
+        if model.optimizer is None:
+            model.optimizer = self._build_optimizer(model)
+        dataset.actions_before_epoch()
+        model.train()
+        losses = []
+        dl = DataLoader(dataset, batch_size=self.batch_size, shuffle=True, num_workers=self.num_workers,
+                        collate_fn=dataset.collate_batch, pin_memory=bool(self.pin_memory))
+        for batch in dl:
+            batch = batch_to_device(batch, model.device)
+            item_ids = batch["item_id"]
+            # per-row candidate permutation drawn from the CPU generator, as the reference does (:189)
+            indices = torch.argsort(torch.rand(*item_ids.shape), dim=-1)
+            rows = torch.arange(item_ids.shape[0]).unsqueeze(-1)
+            batch["item_id"] = item_ids[rows, indices]
+            model.optimizer.zero_grad()
+            out = model(batch)
+            pred = out["prediction"]
+            if pred.dim() == 2:
+                restored = torch.zeros(*pred.shape).to(pred.device)
+                restored[rows, indices] = pred                           # autograd-tracked index_put (:201)
+                out["prediction"] = restored
+            loss = model.loss(out)
+            loss.backward()
+            model.optimizer.step()
+            losses.append(loss.detach().cpu().data.numpy())
+        return float(np.mean(losses))
+
+    def eval_termination(self, criterion: List[float]) -> bool:
+        if len(criterion) > self.early_stop and all(
+                x >= y for x, y in zip(criterion[-self.early_stop:], criterion[-self.early_stop + 1:])):
+            return True
+        return len(criterion) - criterion.index(max(criterion)) > self.early_stop
+
+    def evaluate(self, dataset, topks: list, metrics: list) -> Dict[str, float]:
+        return self.evaluate_method(self.predict(dataset), topks, metrics)
+
+    def predict(self, dataset, save_prediction: bool = False) -> np.ndarray:
+        """helpers/BaseRunner.py:225-252 (uses the model's no-grad ``inference`` hook when present)."""
+        model = dataset.model
+        model.eval()
+        preds = []
+        dl = DataLoader(dataset, batch_size=self.eval_batch_size, shuffle=False, num_workers=self.num_workers,
+                        collate_fn=dataset.collate_batch, pin_memory=bool(self.pin_memory))
+        for batch in dl:
+            batch = batch_to_device(batch, model.device)
+            fn = model.inference if hasattr(model, "inference") else model
+            preds.extend(fn(batch)["prediction"].cpu().data.numpy())
+        preds = np.array(preds)
+        if model.test_all:
+            rows, cols = [], []
+            for i, u in enumerate(dataset.data["user_id"]):
+                clicked = list(dataset.corpus.train_clicked_set[u] | dataset.corpus.residual_clicked_set[u])
+                rows.extend([i] * len(clicked))
+                cols.extend(clicked)
+            preds[rows, cols] = -np.inf
+        return preds
+
+    def print_res(self, dataset) -> str:
+        return "(" + format_metric(self.evaluate(dataset, self.topk, self.metrics)) + ")"
