@@ -77,6 +77,10 @@ B2R_API int b2r_rowdot_bwd_query(const float* g, const float* T, const int64_t* 
 /* Plain row gather out[r,:] = T[ids[r],:]  (nn.Embedding forward, e.g. NeuMF.py:63-66, SASRec.py:59) */
 B2R_API int b2r_gather_rows(const float* T, const int64_t* ids, int64_t n_t, float* out, int64_t n, int d,
                     int32_t* err_flag, b2r_stream_t stream);
+/* out[r*out_ld + 0..d) = T[ids[r / ids_div]]: writes into a column block of a wider activation matrix and
+ * repeats each id ids_div times (NeuMF.py:61 repeats user ids over the candidates; :69 concatenates) */
+B2R_API int b2r_gather_rows_strided(const float* T, const int64_t* ids, int64_t n_t, float* out, int out_ld,
+                            int64_t n, int d, int ids_div, int32_t* err_flag, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * BPR loss + closed-form gradient (models/BaseModel.py:175-189; formula SURVEY.md A.4).
@@ -99,6 +103,12 @@ B2R_API size_t b2r_plan_workspace_bytes(int64_t n, int64_t n_rows);
 B2R_API int b2r_plan_build(const int64_t* ids, int64_t n, int64_t n_rows,
                    uint32_t* sorted_key, uint32_t* sorted_pos, int32_t* seg_start, int32_t* n_uniq,
                    void* ws, size_t ws_bytes, int32_t* err_flag, b2r_stream_t stream);
+/* same, but positions p < ignore_n whose id equals ignore_id are dropped from the gradient (they get the
+ * sentinel key n_rows, which b2r_segment_apply skips): the right-padding of SASRec histories, whose
+ * gradient is exactly zero in the reference (SASRec.py:74 masks them) */
+B2R_API int b2r_plan_build_ex(const int64_t* ids, int64_t n, int64_t n_rows, int64_t ignore_id, int64_t ignore_n,
+                      uint32_t* sorted_key, uint32_t* sorted_pos, int32_t* seg_start, int32_t* n_uniq,
+                      void* ws, size_t ws_bytes, int32_t* err_flag, b2r_stream_t stream);
 
 /* One contribution stream into a table gradient: position p (0 <= p < n) contributes
  *      coef[p] * src[row(p), :]      with   row(p) = src_id ? src_id[p / div] : p / div
@@ -111,7 +121,7 @@ typedef struct {
     const int64_t* src_id;
     int64_t        n;
     int32_t        div;
-    int32_t        _pad;
+    int32_t        ld;             /* leading dimension of src in floats (0 = d) */
 } b2r_grad_source;
 
 /* Optimizer applied to the touched rows (helpers/BaseRunner.py:110-114 builds torch.optim.<name>;
@@ -130,7 +140,7 @@ typedef struct {
  * replaces embedding_dense_backward + grad zero-fill + the embedding part of optimizer.step()
  * (helpers/BaseRunner.py:193,205,206). */
 B2R_API int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sorted_pos, const int32_t* seg_start,
-                      const int32_t* n_uniq, int64_t n, int d,
+                      const int32_t* n_uniq, int64_t n, int64_t n_rows, int d,
                       const b2r_grad_source* s0, const b2r_grad_source* s1,
                       int mode, int64_t* uniq_rows, float* grad_rows, float* dense,
                       float* W, float* m, float* v, const b2r_optim* opt, b2r_stream_t stream);
@@ -144,6 +154,66 @@ B2R_API int b2r_scatter_add_atomic(const int64_t* ids, int64_t n_rows, const b2r
 B2R_API int b2r_dense_optim(float* W, const float* grad, float* m, float* v, int64_t numel,
                     const b2r_optim* opt, b2r_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense layers (fp32 CUDA-core SGEMM with fused epilogues) -- the MLP tower of models/general/NeuMF.py:69-75
+ * and the q/k/v + feed-forward Linear layers of utils/layers.py:26-28,106-107.  W is a torch nn.Linear
+ * weight [N, K] row-major (its leading dimension may exceed K only through the pointer/ld pairs of X, Y).
+ *   fwd        : Y[M,N] = act(X[M,K] W^T + bias),  relu != 0 applies ReLU
+ *   bwd_input  : dX[M,K] = (dY * [relu_out > 0]) W          (relu_out = the layer's saved output, or NULL)
+ *   bwd_weight : dW[N,K] = (dY * [relu_out > 0])^T X ; dbias[N] = column sums (NULL to skip); split over M
+ *                in fixed chunks whose partial sums are added in order -> bit-reproducible
+ * relu_out, when given, must share dY's leading dimension.
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API int b2r_linear_fwd(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy,
+                   int64_t M, int N, int K, int relu, b2r_stream_t stream);
+B2R_API int b2r_linear_bwd_input(const float* dY, int lddy, const float* relu_out, const float* W, float* dX, int lddx,
+                         int64_t M, int N, int K, b2r_stream_t stream);
+B2R_API size_t b2r_linear_bwd_weight_workspace_bytes(int64_t M, int N, int K);
+B2R_API int b2r_linear_bwd_weight(const float* dY, int lddy, const float* relu_out, const float* X, int ldx,
+                          float* dW, float* dbias, int64_t M, int N, int K, void* ws, size_t ws_bytes,
+                          b2r_stream_t stream);
+
+/* y = LayerNorm(x + res) * gamma + beta, eps inside the sqrt, biased variance (utils/layers.py:113,117 via
+ * nn.LayerNorm); mean/rstd [rows] are saved for the backward.  Backward returns dz (gradient of x + res, to be
+ * used for both addends) and dgamma/dbeta (fixed-order two-stage reduction).  d <= 256 in the backward. */
+B2R_API int b2r_add_layernorm_fwd(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                          float* mean, float* rstd, int64_t rows, int d, float eps, b2r_stream_t stream);
+B2R_API size_t b2r_add_layernorm_bwd_workspace_bytes(int64_t rows, int d);
+B2R_API int b2r_add_layernorm_bwd(const float* dy, const float* x, const float* res, const float* gamma,
+                          const float* mean, const float* rstd, float* dz, float* dgamma, float* dbeta,
+                          int64_t rows, int d, void* ws, size_t ws_bytes, b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SASRec sequence kernels (models/sequential/SASRec.py:51-86, utils/layers.py:34-63).
+ *   embed_history : x[b,t,:] = I[hist[b,t]] + P[(len[b]-t) * (hist[b,t] > 0)]; pos_out (optional) gets the
+ *                   position index used per element                                    (SASRec.py:58-66)
+ *   attention_fwd : causal multi-head attention, heads = contiguous d/H chunks, scores / sqrt(d/H),
+ *                   softmax over keys j <= i, no output projection; q,k,v rows at ld stride (layers.py:52-63)
+ *   attention_bwd : recomputes the probabilities; writes dq, dk, dv rows at ldg stride.  L <= 128.
+ *   select_last   : h[b] = y[b, len[b]-1] * (hist[b, len[b]-1] > 0)                    (SASRec.py:74-76)
+ *   small_table_grad : dense gradient of a small table shared by many positions (the position table):
+ *                   dense_out[id] = sum_{r: ids[r]=id} src[r], fixed order, no atomics.
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API int b2r_embed_history(const float* I, int64_t n_items, const float* P, int64_t n_pos, const int64_t* hist,
+                      const int64_t* lengths, float* x, int64_t* pos_out, int B, int L, int d,
+                      int32_t* err_flag, b2r_stream_t stream);
+B2R_API int b2r_attention_fwd(const float* q, const float* k, const float* v, int ld, float* ctx, int B, int L, int d,
+                      int H, b2r_stream_t stream);
+B2R_API int b2r_attention_bwd(const float* q, const float* k, const float* v, int ld, const float* dctx, float* dq,
+                      float* dk, float* dv, int ldg, int B, int L, int d, int H, b2r_stream_t stream);
+B2R_API int b2r_select_last(const float* y, const int64_t* hist, const int64_t* lengths, float* h, int B, int L,
+                    int d, b2r_stream_t stream);
+B2R_API int b2r_select_last_bwd(const float* dh, const int64_t* hist, const int64_t* lengths, float* dy, int B, int L,
+                        int d, b2r_stream_t stream);
+B2R_API size_t b2r_small_table_grad_workspace_bytes(int64_t n, int n_rows, int d);
+B2R_API int b2r_small_table_grad(const float* src, int ld, const int64_t* ids, int64_t n, int n_rows, int d,
+                         float* dense_out, void* ws, size_t ws_bytes, b2r_stream_t stream);
+
+/* out[r,k] = a[r,k] * w[k]   and   out[k] = sum_r a[r,k] * b[r,k]   (the GMF half of NeuMF's final Linear,
+ * models/general/NeuMF.py:68,74-75, and its weight gradient) */
+B2R_API int b2r_colscale(const float* a, const float* w, float* out, int64_t rows, int d, b2r_stream_t stream);
+B2R_API int b2r_colsum_prod(const float* a, const float* b, float* out, int64_t rows, int d, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * One whole BPRMF training step enqueued from C (no Python between kernels):

@@ -140,15 +140,15 @@ extern "C" int b2r_bprmf_train_step(const b2r_bprmf_tables* t, const int64_t* ui
 
     // join, then the fused backward+optimizer on each table (item table first; it only reads the q snapshot)
     B2R_CUDA_OK(cudaStreamWaitEvent(main_s, side->join, 0));
-    b2r_grad_source si{q, g, nullptr, n, C, 0};
+    b2r_grad_source si{q, g, nullptr, n, C, 0 /* ld = d */};
     profile_begin(B2R_PROF_SEGMENT_I, main_s);
-    rc = b2r_segment_apply(ik, ip, is, inu, n, d, &si, nullptr, 2, nullptr, nullptr, nullptr, t->I, t->Im, t->Iv,
+    rc = b2r_segment_apply(ik, ip, is, inu, n, t->n_items, d, &si, nullptr, 2, nullptr, nullptr, nullptr, t->I, t->Im, t->Iv,
                            opt, main_s);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_SEGMENT_I, main_s);
     b2r_grad_source su{dQ, nullptr, nullptr, B, 1, 0};
     profile_begin(B2R_PROF_SEGMENT_U, main_s);
-    rc = b2r_segment_apply(uk, up, us, unu, B, d, &su, nullptr, 2, nullptr, nullptr, nullptr, t->U, t->Um, t->Uv,
+    rc = b2r_segment_apply(uk, up, us, unu, B, t->n_users, d, &su, nullptr, 2, nullptr, nullptr, nullptr, t->U, t->Um, t->Uv,
                            opt, main_s);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_SEGMENT_U, main_s);

@@ -15,9 +15,12 @@ namespace b2r {
 
 __global__ void __launch_bounds__(256)
 k_plan_keys(const int64_t* __restrict__ ids, int64_t n, int64_t n_rows, uint32_t* __restrict__ key,
-            uint32_t* __restrict__ pos, int32_t* err_flag) {
+            uint32_t* __restrict__ pos, int32_t* err_flag, int64_t ignore_id, int64_t ignore_n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        key[i] = (uint32_t)checked_id(ids[i], n_rows, err_flag);
+        const int64_t id = ids[i];
+        // positions [0, ignore_n) holding ignore_id contribute nothing (e.g. right-padding of a history): they
+        // get the sentinel key n_rows, sort to the end, and the segment kernels skip rows >= n_rows
+        key[i] = (i < ignore_n && id == ignore_id) ? (uint32_t)n_rows : (uint32_t)checked_id(id, n_rows, err_flag);
         pos[i] = (uint32_t)i;
     }
 }
@@ -27,9 +30,9 @@ struct RunHead {
     __host__ __device__ bool operator()(const int32_t& i) const { return i == 0 || key[i] != key[i - 1]; }
 };
 
-static int key_bits(int64_t n_rows) {
+static int key_bits(int64_t n_rows) {     // keys are in [0, n_rows] (n_rows itself = the "ignored" sentinel)
     int bits = 1;
-    while (bits < 32 && ((int64_t)1 << bits) < n_rows) ++bits;
+    while (bits < 32 && ((int64_t)1 << bits) <= n_rows) ++bits;
     return bits;
 }
 
@@ -71,11 +74,18 @@ extern "C" size_t b2r_plan_workspace_bytes(int64_t n, int64_t n_rows) {
 extern "C" int b2r_plan_build(const int64_t* ids, int64_t n, int64_t n_rows, uint32_t* sorted_key,
                               uint32_t* sorted_pos, int32_t* seg_start, int32_t* n_uniq, void* ws,
                               size_t ws_bytes, int32_t* err_flag, b2r_stream_t stream) {
+    return b2r_plan_build_ex(ids, n, n_rows, -1, 0, sorted_key, sorted_pos, seg_start, n_uniq, ws, ws_bytes, err_flag,
+                             stream);
+}
+
+extern "C" int b2r_plan_build_ex(const int64_t* ids, int64_t n, int64_t n_rows, int64_t ignore_id, int64_t ignore_n,
+                                 uint32_t* sorted_key, uint32_t* sorted_pos, int32_t* seg_start, int32_t* n_uniq,
+                                 void* ws, size_t ws_bytes, int32_t* err_flag, b2r_stream_t stream) {
     B2R_REQUIRE(ids && sorted_key && sorted_pos && seg_start && n_uniq && ws, B2R_E_BADARG,
                 "b2r_plan_build: null pointer");
     B2R_REQUIRE(n > 0 && n <= 0x7fffffff, B2R_E_BADARG, "b2r_plan_build: n must be in [1, 2^31) (n=%lld)",
                 (long long)n);
-    B2R_REQUIRE(n_rows > 0 && n_rows <= 0xffffffffLL, B2R_E_UNSUPPORTED,
+    B2R_REQUIRE(n_rows > 0 && n_rows < 0xffffffffLL, B2R_E_UNSUPPORTED,
                 "b2r_plan_build: n_rows must fit 32 bits (n_rows=%lld)", (long long)n_rows);
     PlanLayout L;
     int rc = plan_layout(n, n_rows, &L);
@@ -94,7 +104,7 @@ extern "C" int b2r_plan_build(const int64_t* ids, int64_t n, int64_t n_rows, uin
     int grid = (int)((n + 255) / 256);
     const int cap = sm_count() * 8;
     if (grid > cap) grid = cap;
-    k_plan_keys<<<grid, 256, 0, s>>>(ids, n, n_rows, key_in, pos_in, err_flag);
+    k_plan_keys<<<grid, 256, 0, s>>>(ids, n, n_rows, key_in, pos_in, err_flag, ignore_id, ignore_n);
     B2R_LAUNCH_OK("k_plan_keys");
 
     size_t tmp_bytes = L.cub_bytes;

@@ -166,7 +166,7 @@ k_rowdot_bwd_query_generic(const float* __restrict__ g, const float* __restrict_
 template <int LPR, int RCH>
 __global__ void __launch_bounds__(kThreads)
 k_gather_rows(const float* __restrict__ T, const int64_t* __restrict__ ids, int64_t n_t,
-              float* __restrict__ out, int64_t n, int32_t* err_flag) {
+              float* __restrict__ out, int64_t out_ld, int64_t n, int ids_div, int32_t* err_flag) {
     static_assert(RCH <= LPR, "ids of a chunk are loaded one per lane");
     constexpr int D = LPR * 4;
     constexpr int GPC = kThreads / LPR;
@@ -180,7 +180,7 @@ k_gather_rows(const float* __restrict__ T, const int64_t* __restrict__ ids, int6
         const int64_t r0 = ch * RCH;
         const int nr = (ch < nchunks) ? (int)min((int64_t)RCH, n - r0) : 0;
         int64_t my_id = 0;
-        if (sub < nr) my_id = checked_id(ids[r0 + sub], n_t, err_flag);
+        if (sub < nr) my_id = checked_id(ids[(r0 + sub) / ids_div], n_t, err_flag);
         float4 r[RCH];
 #pragma unroll
         for (int k = 0; k < RCH; ++k) {
@@ -189,19 +189,19 @@ k_gather_rows(const float* __restrict__ T, const int64_t* __restrict__ ids, int6
         }
 #pragma unroll
         for (int k = 0; k < RCH; ++k)
-            if (k < nr) st4(out + (r0 + k) * D + sub * 4, r[k]);
+            if (k < nr) st4(out + (r0 + k) * out_ld + sub * 4, r[k]);
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
 k_gather_rows_generic(const float* __restrict__ T, const int64_t* __restrict__ ids, int64_t n_t,
-                      float* __restrict__ out, int64_t n, int d, int32_t* err_flag) {
+                      float* __restrict__ out, int64_t out_ld, int64_t n, int d, int ids_div, int32_t* err_flag) {
     const int lane = threadIdx.x & 31;
     const int d4 = d >> 2;
     for (int64_t r = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); r < n;
          r += (int64_t)gridDim.x * (kThreads / 32)) {
-        const int64_t id = checked_id(ids[r], n_t, lane == 0 ? err_flag : nullptr);
-        for (int k = lane; k < d4; k += 32) st4(out + r * d + k * 4, ld_row4(T + id * d + k * 4));
+        const int64_t id = checked_id(ids[r / ids_div], n_t, lane == 0 ? err_flag : nullptr);
+        for (int k = lane; k < d4; k += 32) st4(out + r * out_ld + k * 4, ld_row4(T + id * d + k * 4));
     }
 }
 
@@ -281,8 +281,15 @@ extern "C" int b2r_rowdot_bwd_query(const float* g, const float* T, const int64_
 
 extern "C" int b2r_gather_rows(const float* T, const int64_t* ids, int64_t n_t, float* out, int64_t n,
                                int d, int32_t* err_flag, b2r_stream_t stream) {
+    return b2r_gather_rows_strided(T, ids, n_t, out, d, n, d, 1, err_flag, stream);
+}
+
+extern "C" int b2r_gather_rows_strided(const float* T, const int64_t* ids, int64_t n_t, float* out, int out_ld,
+                                       int64_t n, int d, int ids_div, int32_t* err_flag, b2r_stream_t stream) {
     B2R_REQUIRE(T && ids && out, B2R_E_BADARG, "b2r_gather_rows: null pointer");
     B2R_REQUIRE(n >= 0 && d > 0 && d % 4 == 0, B2R_E_BADARG, "b2r_gather_rows: need n >= 0, d %% 4 == 0");
+    B2R_REQUIRE(out_ld >= d && out_ld % 4 == 0 && ids_div >= 1, B2R_E_BADARG,
+                "b2r_gather_rows: out_ld=%d must be >= d and a multiple of 4, ids_div=%d >= 1", out_ld, ids_div);
     B2R_REQUIRE(aligned16(T) && aligned16(out), B2R_E_BADARG, "b2r_gather_rows: 16-byte alignment");
     if (n == 0) return 0;
     cudaStream_t s = as_stream(stream);
@@ -290,12 +297,13 @@ extern "C" int b2r_gather_rows(const float* T, const int64_t* ids, int64_t n_t, 
     const int64_t nchunks = (n + RCH - 1) / RCH;
 #define B2R_GATHER(LPR)                                                                                \
     k_gather_rows<LPR, RCH><<<grid_for((nchunks + kThreads / LPR - 1) / (kThreads / LPR)), kThreads, 0, s>>>( \
-        T, ids, n_t, out, n, err_flag)
+        T, ids, n_t, out, out_ld, n, ids_div, err_flag)
     if (d == 32) B2R_GATHER(8);
     else if (d == 64) B2R_GATHER(16);
     else if (d == 128) B2R_GATHER(32);
     else
-        k_gather_rows_generic<<<grid_for((n + 7) / 8), kThreads, 0, s>>>(T, ids, n_t, out, n, d, err_flag);
+        k_gather_rows_generic<<<grid_for((n + 7) / 8), kThreads, 0, s>>>(T, ids, n_t, out, out_ld, n, d, ids_div,
+                                                                         err_flag);
 #undef B2R_GATHER
     B2R_LAUNCH_OK("k_gather_rows");
     return 0;

@@ -17,6 +17,7 @@ struct Src {
     const int64_t* src_id;
     int64_t n;
     int32_t div;
+    int32_t ld;
 };
 
 __device__ __forceinline__ void contribution(const Src& s0, const Src& s1, uint32_t p, int64_t& row, float& c) {
@@ -54,7 +55,7 @@ __device__ __forceinline__ void optim_update(const b2r_optim& o, float4& w, floa
 template <int LPR, int MODE>
 __global__ void __launch_bounds__(256)
 k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restrict__ sorted_pos,
-                const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n,
+                const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n, int64_t n_rows,
                 Src s0, Src s1, int64_t* __restrict__ uniq_rows, float* __restrict__ grad_rows,
                 float* __restrict__ dense, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V,
                 b2r_optim opt) {
@@ -67,6 +68,10 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
         const int beg = seg_start[u];
         const int end = (u + 1 < nu) ? seg_start[u + 1] : n;
         const int64_t row = sorted_key[beg];
+        if (row >= n_rows) {                      // sentinel segment of ignored positions (always the last one)
+            if (MODE == 0 && sub == 0) uniq_rows[u] = row;
+            continue;
+        }
         float4 w, m, v;
         if (MODE == 2) {
             w = ld4(W + row * D + sub * 4);
@@ -81,7 +86,7 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
             float c;
             contribution(s0, s1, sorted_pos[j], r, c);
             const Src& s = ((int64_t)sorted_pos[j] < s0.n) ? s0 : s1;
-            fma4(acc, c, ld4(s.src + r * D + sub * 4));
+            fma4(acc, c, ld4(s.src + r * s.ld + sub * 4));
         }
         if (MODE == 0) {
             if (sub == 0) uniq_rows[u] = row;
@@ -102,8 +107,8 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_segment_apply_generic(const uint32_t* __restrict__ sorted_key, const uint32_t* __restrict__ sorted_pos,
-                        const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n, int d,
-                        Src s0, Src s1, int64_t* __restrict__ uniq_rows, float* __restrict__ grad_rows,
+                        const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n,
+                        int64_t n_rows, int d, Src s0, Src s1, int64_t* __restrict__ uniq_rows, float* __restrict__ grad_rows,
                         float* __restrict__ dense, float* __restrict__ W, float* __restrict__ M,
                         float* __restrict__ V, b2r_optim opt) {
     const int lane = threadIdx.x & 31;
@@ -114,6 +119,7 @@ k_segment_apply_generic(const uint32_t* __restrict__ sorted_key, const uint32_t*
         const int end = (u + 1 < nu) ? seg_start[u + 1] : n;
         const int64_t row = sorted_key[beg];
         if (MODE == 0 && lane == 0) uniq_rows[u] = row;
+        if (row >= n_rows) continue;
         for (int k = lane; k < d4; k += 32) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int j = beg; j < end; ++j) {
@@ -121,7 +127,7 @@ k_segment_apply_generic(const uint32_t* __restrict__ sorted_key, const uint32_t*
                 float c;
                 contribution(s0, s1, sorted_pos[j], r, c);
                 const Src& s = ((int64_t)sorted_pos[j] < s0.n) ? s0 : s1;
-                fma4(acc, c, ld4(s.src + r * d + k * 4));
+                fma4(acc, c, ld4(s.src + r * s.ld + k * 4));
             }
             if (MODE == 0) {
                 st4(grad_rows + (int64_t)u * d + k * 4, acc);
@@ -154,7 +160,7 @@ k_scatter_add_atomic(const int64_t* __restrict__ ids, int64_t n_rows, Src s, int
         if (s.src_id != nullptr) r = s.src_id[r];
         const float c = (s.coef != nullptr) ? s.coef[p] : 1.f;
         for (int k = lane; k < d4; k += 32) {
-            const float4 x = ld4(s.src + r * d + k * 4);
+            const float4 x = ld4(s.src + r * s.ld + k * 4);
             float* a = dense + dst * d + k * 4;
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(c * x.x), "f"(c * x.y),
                          "f"(c * x.z), "f"(c * x.w)
@@ -190,14 +196,15 @@ k_dense_optim(float* __restrict__ W, const float* __restrict__ G, float* __restr
     }
 }
 
-static Src to_src(const b2r_grad_source* s) {
-    Src r{nullptr, nullptr, nullptr, 0, 1};
+static Src to_src(const b2r_grad_source* s, int d) {
+    Src r{nullptr, nullptr, nullptr, 0, 1, d};
     if (s) {
         r.src = s->src;
         r.coef = s->coef;
         r.src_id = s->src_id;
         r.n = s->n;
         r.div = s->div < 1 ? 1 : s->div;
+        r.ld = s->ld > 0 ? s->ld : d;
     }
     return r;
 }
@@ -207,7 +214,8 @@ static Src to_src(const b2r_grad_source* s) {
 using namespace b2r;
 
 extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sorted_pos, const int32_t* seg_start,
-                                 const int32_t* n_uniq, int64_t n, int d, const b2r_grad_source* s0,
+                                 const int32_t* n_uniq, int64_t n, int64_t n_rows, int d,
+                                 const b2r_grad_source* s0,
                                  const b2r_grad_source* s1, int mode, int64_t* uniq_rows, float* grad_rows,
                                  float* dense, float* W, float* m, float* v, const b2r_optim* opt,
                                  b2r_stream_t stream) {
@@ -234,7 +242,7 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
         return set_error(B2R_E_BADARG, "b2r_segment_apply: mode %d", mode);
     }
     cudaStream_t s = as_stream(stream);
-    const Src a = to_src(s0), b = to_src(s1);
+    const Src a = to_src(s0, d), b = to_src(s1, d);
     const int nn = (int)n;
     // n_uniq lives on the device: size the grid for the worst case (n unique rows), capped persistent
 #define B2R_SEG(LPR, MODE)                                                                             \
@@ -243,7 +251,7 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
         int64_t need = (n + GPC - 1) / GPC;                                                            \
         const int64_t cap = (int64_t)sm_count() * 16;                                                  \
         const int grid = (int)(need < cap ? need : cap);                                               \
-        k_segment_apply<LPR, MODE><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, a, b, \
+        k_segment_apply<LPR, MODE><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, n_rows, a, b, \
                                                         uniq_rows, grad_rows, dense, W, m, v, o);      \
     } while (0)
 #define B2R_SEG_D(MODE)                                                                                \
@@ -255,7 +263,7 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
             int64_t need = (n + 7) / 8;                                                                \
             const int64_t cap = (int64_t)sm_count() * 16;                                              \
             const int grid = (int)(need < cap ? need : cap);                                           \
-            k_segment_apply_generic<MODE><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, d, \
+            k_segment_apply_generic<MODE><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, n_rows, d, \
                                                                a, b, uniq_rows, grad_rows, dense, W, m, v, o); \
         }                                                                                              \
     } while (0)
@@ -273,7 +281,7 @@ extern "C" int b2r_scatter_add_atomic(const int64_t* ids, int64_t n_rows, const 
     B2R_REQUIRE(ids && src && src->src && dense, B2R_E_BADARG, "b2r_scatter_add_atomic: null pointer");
     B2R_REQUIRE(d > 0 && d % 4 == 0 && n_rows > 0, B2R_E_BADARG, "b2r_scatter_add_atomic: bad d or n_rows");
     if (src->n <= 0) return 0;
-    const Src a = to_src(src);
+    const Src a = to_src(src, d);
     int64_t need = (a.n + 7) / 8;
     const int64_t cap = (int64_t)sm_count() * 16;
     k_scatter_add_atomic<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(ids, n_rows, a, d, dense,

@@ -18,7 +18,7 @@ c_f32p = C.c_void_p
 class GradSource(C.Structure):
     """b2r_grad_source (include/b200rec.h)"""
     _fields_ = [("src", C.c_void_p), ("coef", C.c_void_p), ("src_id", C.c_void_p),
-                ("n", C.c_int64), ("div", C.c_int32), ("_pad", C.c_int32)]
+                ("n", C.c_int64), ("div", C.c_int32), ("ld", C.c_int32)]
 
 
 class Optim(C.Structure):
@@ -54,7 +54,11 @@ SIGNATURES = {
     "b2r_plan_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "b2r_plan_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
-    "b2r_segment_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+    "b2r_plan_build_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "b2r_gather_rows_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64,
+                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b2r_segment_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
                                     C.POINTER(GradSource), C.POINTER(GradSource), C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(Optim), C.c_void_p]),
@@ -62,6 +66,31 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "b2r_dense_optim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.POINTER(Optim), C.c_void_p]),
+    "b2r_linear_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2r_linear_bwd_input": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "b2r_linear_bwd_weight_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "b2r_linear_bwd_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
+    "b2r_add_layernorm_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "b2r_add_layernorm_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
+    "b2r_add_layernorm_bwd": (C.c_int, [C.c_void_p] * 9 + [C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b2r_embed_history": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b2r_attention_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p]),
+    "b2r_attention_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p]),
+    "b2r_select_last": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2r_select_last_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2r_small_table_grad_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "b2r_small_table_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b2r_colscale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "b2r_colsum_prod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b2r_bprmf_step_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]),
     "b2r_bprmf_train_step": (C.c_int, [C.POINTER(BprmfTables), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.POINTER(Optim), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,

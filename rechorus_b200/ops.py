@@ -154,15 +154,16 @@ class Source:
     coef: Optional[torch.Tensor] = None    # [n] float32
     src_id: Optional[torch.Tensor] = None  # int64
     div: int = 1
+    ld: int = 0                            # leading dimension of src in floats (0: d)
 
     def c_struct(self) -> _lib.GradSource:
-        return _lib.GradSource(_p(self.src), _p(self.coef), _p(self.src_id), self.n, self.div, 0)
+        return _lib.GradSource(_p(self.src), _p(self.coef), _p(self.src_id), self.n, self.div, self.ld)
 
 
 class IndexPlan:
     """Sorted, de-duplicated view of the ids a batch touches in one table (b2r_plan_build)."""
 
-    def __init__(self, ids: torch.Tensor, n_rows: int):
+    def __init__(self, ids: torch.Tensor, n_rows: int, ignore_id: int = -1, ignore_n: int = 0):
         _need_cuda(ids)
         ids = _i64c(ids.reshape(-1), "ids")
         n = ids.numel()
@@ -179,9 +180,9 @@ class IndexPlan:
         if nbytes == 0:
             raise _lib.B200RecError(f"b2r_plan_workspace_bytes({n}, {n_rows}) = 0: " + L.b2r_last_error().decode())
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(L.b2r_plan_build(_p(ids), n, self.n_rows, _p(self.sorted_key), _p(self.sorted_pos),
-                                    _p(self.seg_start), _p(self.n_uniq), _p(ws), nbytes, _p(err_flag(dev)),
-                                    _stream()), "b2r_plan_build")
+        _lib.check(L.b2r_plan_build_ex(_p(ids), n, self.n_rows, int(ignore_id), int(ignore_n), _p(self.sorted_key),
+                                       _p(self.sorted_pos), _p(self.seg_start), _p(self.n_uniq), _p(ws), nbytes,
+                                       _p(err_flag(dev)), _stream()), "b2r_plan_build_ex")
         self._ws = ws   # keep alive until the stream has consumed it
 
     def count(self) -> int:
@@ -198,7 +199,7 @@ class IndexPlan:
         s1 = sources[1].c_struct() if len(sources) == 2 else None
         L = _lib.load()
         _lib.check(L.b2r_segment_apply(_p(self.sorted_key), _p(self.sorted_pos), _p(self.seg_start),
-                                       _p(self.n_uniq), self.n, d, C.byref(s0),
+                                       _p(self.n_uniq), self.n, self.n_rows, d, C.byref(s0),
                                        C.byref(s1) if s1 is not None else None, mode, _p(uniq), _p(rows),
                                        _p(dense), _p(W), _p(m), _p(v),
                                        C.byref(opt) if opt is not None else None, _stream()),
@@ -210,6 +211,8 @@ class IndexPlan:
         rows = torch.empty((self.n, d), dtype=torch.float32, device=self.device)
         self._apply(d, sources, 0, uniq=uniq, rows=rows)
         nu = self.count()
+        if nu > 0 and int(uniq[nu - 1].item()) >= self.n_rows:      # trailing sentinel run of ignored positions
+            nu -= 1
         return uniq[:nu], rows[:nu]
 
     def add_to_dense(self, dense: torch.Tensor, sources: Sequence[Source]) -> None:
@@ -253,12 +256,14 @@ def table_mode(param: torch.Tensor) -> str:
     return getattr(param, "_b2r_mode", "dense")
 
 
-def _table_grad(table: torch.Tensor, ids: torch.Tensor, source: Source) -> Optional[torch.Tensor]:
+def _table_grad(table: torch.Tensor, ids: torch.Tensor, source: Source, ignore_id: int = -1
+                ) -> Optional[torch.Tensor]:
+    """ignore_id: positions holding this id contribute exactly zero (padding) and are dropped from the plan"""
     mode = table_mode(table)
     if mode == "fused":
-        table._b2r_pending.append((ids.reshape(-1), source))
+        table._b2r_pending.append((ids.reshape(-1), source, ignore_id))
         return None
-    plan = IndexPlan(ids, table.shape[0])
+    plan = IndexPlan(ids, table.shape[0], ignore_id, ids.numel() if ignore_id >= 0 else 0)
     if mode == "sparse":
         uniq, rows = plan.reduce_rows(table.shape[1], [source])
         return torch.sparse_coo_tensor(uniq.unsqueeze(0), rows, size=tuple(table.shape), is_coalesced=True)
@@ -376,3 +381,300 @@ def bprmf_train_step(U: torch.nn.Parameter, I: torch.nn.Parameter, optimizer, ui
     _lib.check(L.b2r_bprmf_train_step(C.byref(tables), _p(uid), _p(iid), B, Cn, C.byref(opt), _p(loss), _p(ws),
                                       ws.numel(), _p(err_flag(U.device)), _stream()), "b2r_bprmf_train_step")
     return loss
+
+
+# --------------------------------------------------------------------------------------------------
+# dense layers (NeuMF MLP tower, SASRec q/k/v + FFN, LayerNorm, attention) -- kernels + autograd nodes
+# --------------------------------------------------------------------------------------------------
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _rows_ld(t: torch.Tensor) -> Tuple[int, int]:
+    """(rows, leading dimension) of a 2-D float32 tensor whose last dim is contiguous"""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("expected a 2-D tensor with a contiguous last dimension")
+    return t.shape[0], t.stride(0)
+
+
+def linear_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+    """y = act(x W^T + b); x [M, K] (row stride may exceed K), W [N, K] contiguous (nn.Linear layout)."""
+    _need_cuda(x, W)
+    M, ldx = _rows_ld(x)
+    N, K = W.shape
+    W = _f32c(W, "W")
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    L = _lib.load()
+    _lib.check(L.b2r_linear_fwd(_p(x), ldx, _p(W), _p(bias), _p(y), N, M, N, K, 1 if relu else 0, _stream()),
+               "b2r_linear_fwd")
+    return y
+
+
+def linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, y_relu: Optional[torch.Tensor],
+               need_dx: bool, need_dw: bool, need_db: bool):
+    """gradients of y = act(x W^T + b) given dy; y_relu = saved post-ReLU output (None when no ReLU)."""
+    M, lddy = _rows_ld(dy)
+    _, ldx = _rows_ld(x)
+    N, K = W.shape
+    L = _lib.load()
+    dx = dW = db = None
+    if y_relu is not None and _rows_ld(y_relu)[1] != lddy:
+        y_relu = y_relu.contiguous()
+        dy = dy.contiguous()
+        lddy = N
+    if need_dx:
+        dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+        _lib.check(L.b2r_linear_bwd_input(_p(dy), lddy, _p(y_relu), _p(W), _p(dx), K, M, N, K, _stream()),
+                   "b2r_linear_bwd_input")
+    if need_dw or need_db:
+        dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+        db = torch.empty((N,), dtype=torch.float32, device=dy.device) if need_db else None
+        nbytes = L.b2r_linear_bwd_weight_workspace_bytes(M, N, K)
+        ws = _ws(nbytes, dy.device)
+        _lib.check(L.b2r_linear_bwd_weight(_p(dy), lddy, _p(y_relu), _p(x), ldx, _p(dW), _p(db), M, N, K, _p(ws),
+                                           ws.numel(), _stream()), "b2r_linear_bwd_weight")
+    return dx, dW, db
+
+
+class _Linear(torch.autograd.Function):
+    """nn.Linear (+ optional ReLU) on the library's SGEMM: NeuMF.py:70 / layers.py:26-28,106-107."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, relu):
+        shape = x.shape
+        x2 = x.reshape(-1, shape[-1])
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        y = linear_fwd(x2, W, bias, relu)
+        ctx.save_for_backward(x2, W, y if relu else None)
+        ctx.has_bias, ctx.shape = bias is not None, shape
+        return y.view(*shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, y_relu = ctx.saved_tensors
+        dy2 = _f32c(dy.reshape(-1, W.shape[0]), "dy")
+        dx, dW, db = linear_bwd(dy2, x2, W, y_relu, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                ctx.has_bias and ctx.needs_input_grad[2])
+        if dx is not None:
+            dx = dx.view(*ctx.shape)
+        return dx, dW, db, None
+
+
+def linear(x, W, bias=None, relu=False):
+    return _Linear.apply(x, W, bias, relu)
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """LayerNorm(x + res) with affine (layers.py:113,117)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps):
+        d = x.shape[-1]
+        x2, r2 = _f32c(x.reshape(-1, d), "x"), _f32c(res.reshape(-1, d), "res")
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        L = _lib.load()
+        _lib.check(L.b2r_add_layernorm_fwd(_p(x2), _p(r2), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, d,
+                                           float(eps), _stream()), "b2r_add_layernorm_fwd")
+        ctx.save_for_backward(x2, r2, gamma, mean, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, r2, gamma, mean, rstd = ctx.saved_tensors
+        d = x2.shape[1]
+        rows = x2.shape[0]
+        dy2 = _f32c(dy.reshape(-1, d), "dy")
+        dz = torch.empty_like(x2)
+        dg = torch.empty(d, dtype=torch.float32, device=dy.device)
+        db = torch.empty(d, dtype=torch.float32, device=dy.device)
+        L = _lib.load()
+        ws = _ws(L.b2r_add_layernorm_bwd_workspace_bytes(rows, d), dy.device)
+        _lib.check(L.b2r_add_layernorm_bwd(_p(dy2), _p(x2), _p(r2), _p(gamma), _p(mean), _p(rstd), _p(dz), _p(dg),
+                                           _p(db), rows, d, _p(ws), ws.numel(), _stream()), "b2r_add_layernorm_bwd")
+        dz = dz.view(ctx.shape)
+        return dz, dz, dg, db, None
+
+
+def add_layernorm(x, res, gamma, beta, eps=1e-5):
+    return _AddLayerNorm.apply(x, res, gamma, beta, eps)
+
+
+class _CausalAttention(torch.autograd.Function):
+    """layers.py:52-63 for q,k,v [B, L, d] with H heads (contiguous d/H chunks), causal mask, no W_o."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, H):
+        B, Ln, d = q.shape
+        q, k, v = _f32c(q, "q"), _f32c(k, "k"), _f32c(v, "v")
+        out = torch.empty((B, Ln, d), dtype=torch.float32, device=q.device)
+        L = _lib.load()
+        _lib.check(L.b2r_attention_fwd(_p(q), _p(k), _p(v), d, _p(out), B, Ln, d, H, _stream()), "b2r_attention_fwd")
+        ctx.save_for_backward(q, k, v)
+        ctx.H = H
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v = ctx.saved_tensors
+        B, Ln, d = q.shape
+        dout = _f32c(dout, "dctx")
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        L = _lib.load()
+        _lib.check(L.b2r_attention_bwd(_p(q), _p(k), _p(v), d, _p(dout), _p(dq), _p(dk), _p(dv), d, B, Ln, d, ctx.H,
+                                       _stream()), "b2r_attention_bwd")
+        return dq, dk, dv, None
+
+
+def causal_attention(q, k, v, num_heads):
+    return _CausalAttention.apply(q, k, v, num_heads)
+
+
+class _EmbedHistory(torch.autograd.Function):
+    """x = I[hist] + P[(len - t) * valid]  (SASRec.py:58-66); backward: row-sparse scatter into I (padding
+    positions dropped: their gradient is exactly zero) and the dense small-table gradient of P."""
+
+    @staticmethod
+    def forward(ctx, I, P, hist, lengths):
+        hist, lengths = _i64c(hist, "history_items"), _i64c(lengths, "lengths")
+        B, Ln = hist.shape
+        d = I.shape[1]
+        x = torch.empty((B, Ln, d), dtype=torch.float32, device=I.device)
+        pos = torch.empty((B, Ln), dtype=torch.int64, device=I.device)
+        L = _lib.load()
+        _lib.check(L.b2r_embed_history(_p(I), I.shape[0], _p(P), P.shape[0], _p(hist), _p(lengths), _p(x), _p(pos),
+                                       B, Ln, d, _p(err_flag(I.device)), _stream()), "b2r_embed_history")
+        ctx.save_for_backward(hist, pos)
+        ctx.I, ctx.P = I, P
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        hist, pos = ctx.saved_tensors
+        I, P = ctx.I, ctx.P
+        d = I.shape[1]
+        dx2 = _f32c(dx.reshape(-1, d), "dx")
+        gI = gP = None
+        if ctx.needs_input_grad[0]:
+            gI = _table_grad(I, hist, Source(src=dx2, n=hist.numel()), ignore_id=0)
+        if ctx.needs_input_grad[1]:
+            n = pos.numel()
+            gP = torch.empty_like(P)
+            L = _lib.load()
+            ws = _ws(L.b2r_small_table_grad_workspace_bytes(n, P.shape[0], d), dx.device)
+            _lib.check(L.b2r_small_table_grad(_p(dx2), d, _p(pos), n, P.shape[0], d, _p(gP), _p(ws), ws.numel(),
+                                              _stream()), "b2r_small_table_grad")
+        return gI, gP, None, None
+
+
+def embed_history(I, P, hist, lengths):
+    return _EmbedHistory.apply(I, P, hist, lengths)
+
+
+class _SelectLast(torch.autograd.Function):
+    """h[b] = y[b, len[b]-1] * valid  (SASRec.py:74-76)."""
+
+    @staticmethod
+    def forward(ctx, y, hist, lengths):
+        y = _f32c(y, "y")
+        B, Ln, d = y.shape
+        h = torch.empty((B, d), dtype=torch.float32, device=y.device)
+        L = _lib.load()
+        _lib.check(L.b2r_select_last(_p(y), _p(hist), _p(lengths), _p(h), B, Ln, d, _stream()), "b2r_select_last")
+        ctx.save_for_backward(hist, lengths)
+        ctx.shape = (B, Ln, d)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        hist, lengths = ctx.saved_tensors
+        B, Ln, d = ctx.shape
+        dy = torch.empty((B, Ln, d), dtype=torch.float32, device=dh.device)
+        L = _lib.load()
+        _lib.check(L.b2r_select_last_bwd(_p(_f32c(dh, "dh")), _p(hist), _p(lengths), _p(dy), B, Ln, d, _stream()),
+                   "b2r_select_last_bwd")
+        return dy, None, None
+
+
+def select_last(y, hist, lengths):
+    return _SelectLast.apply(y, _i64c(hist, "history_items"), _i64c(lengths, "lengths"))
+
+
+class _ColScale(torch.autograd.Function):
+    """out[r,k] = a[r,k] * w[k]  (the GMF half of NeuMF's bias-free output layer, NeuMF.py:68,74-75)."""
+
+    @staticmethod
+    def forward(ctx, a, w):
+        a, w = _f32c(a, "a"), _f32c(w, "w")
+        out = torch.empty_like(a)
+        L = _lib.load()
+        _lib.check(L.b2r_colscale(_p(a), _p(w), _p(out), a.shape[0], a.shape[1], _stream()), "b2r_colscale")
+        ctx.save_for_backward(a, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, w = ctx.saved_tensors
+        g = _f32c(g, "g")
+        L = _lib.load()
+        da = dw = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty_like(a)
+            _lib.check(L.b2r_colscale(_p(g), _p(w), _p(da), a.shape[0], a.shape[1], _stream()), "b2r_colscale")
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            _lib.check(L.b2r_colsum_prod(_p(g), _p(a), _p(dw), a.shape[0], a.shape[1], _stream()), "b2r_colsum_prod")
+        return da, dw
+
+
+def colscale(a, w):
+    return _ColScale.apply(a, w)
+
+
+class _GatherConcat(torch.autograd.Function):
+    """x[p, :] = [ Tu[uid[p // C]] ; Ti[iid[p]] ]  (NeuMF.py:61-69: repeated user ids + concat), written by two
+    strided gathers into one [B*C, 2d] buffer; backward: one row-sparse scatter per table reading its column
+    block of the dense gradient in place."""
+
+    @staticmethod
+    def forward(ctx, Tu, Ti, uid, iid):
+        uid, iid = _i64c(uid, "user_id"), _i64c(iid, "item_id")
+        B, Cn = iid.shape
+        d = Tu.shape[1]
+        n = B * Cn
+        x = torch.empty((n, 2 * d), dtype=torch.float32, device=Tu.device)
+        L = _lib.load()
+        ef = _p(err_flag(Tu.device))
+        _lib.check(L.b2r_gather_rows_strided(_p(Tu), _p(uid), Tu.shape[0], _p(x), 2 * d, n, d, Cn, ef, _stream()),
+                   "b2r_gather_rows_strided")
+        _lib.check(L.b2r_gather_rows_strided(_p(Ti), _p(iid), Ti.shape[0], x.data_ptr() + 4 * d, 2 * d, n, d, 1, ef,
+                                             _stream()), "b2r_gather_rows_strided")
+        ctx.save_for_backward(uid, iid)
+        ctx.Tu, ctx.Ti = Tu, Ti
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        uid, iid = ctx.saved_tensors
+        Tu, Ti = ctx.Tu, ctx.Ti
+        B, Cn = iid.shape
+        d = Tu.shape[1]
+        n = B * Cn
+        dx = _f32c(dx, "dx")
+        gu = gi = None
+        if ctx.needs_input_grad[0]:
+            # one position per sample-candidate pair, id = uid[p // C]: materialise the repeated ids for the plan
+            rep = uid.repeat_interleave(Cn)
+            gu = _table_grad(Tu, rep, Source(src=dx, n=n, ld=2 * d))
+        if ctx.needs_input_grad[1]:
+            gi = _table_grad(Ti, iid, Source(src=dx[:, d:], n=n, ld=2 * d))
+        return gu, gi, None, None
+
+
+def gather_concat(Tu, Ti, uid, iid):
+    return _GatherConcat.apply(Tu, Ti, uid, iid)

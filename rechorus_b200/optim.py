@@ -72,9 +72,14 @@ class RowSparseOptimizer:
                     continue
                 if len(pend) > 2:
                     raise _lib.B200RecError(f"{e['name']}: more than two gradient streams into one table")
+                # a stream with an ignore id (padding) must come first: the plan drops ignore_id only in a prefix
+                pend.sort(key=lambda x: 0 if x[2] >= 0 else 1)
+                if len(pend) == 2 and pend[1][2] >= 0:
+                    raise _lib.B200RecError(f"{e['name']}: two padded gradient streams into one table")
                 ids = pend[0][0] if len(pend) == 1 else torch.cat([pend[0][0], pend[1][0]])
-                plan = ops.IndexPlan(ids, p.shape[0])
-                plan.apply_optimizer(p.data, e["m"], e["v"], self._opt(e["wd"]), [s for _, s in pend])
+                ign = pend[0][2]
+                plan = ops.IndexPlan(ids, p.shape[0], ign, pend[0][0].numel() if ign >= 0 else 0)
+                plan.apply_optimizer(p.data, e["m"], e["v"], self._opt(e["wd"]), [x[1] for x in pend])
                 pend.clear()
             elif p.grad is not None:
                 if p.grad.is_sparse:

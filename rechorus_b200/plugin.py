@@ -99,6 +99,146 @@ class BPRMFKernels(_KernelModelMixin):
                                     feed_dict["user_id"], feed_dict["item_id"])
 
 
+class NeuMFKernels(_KernelModelMixin):
+    """models/general/NeuMF.py:22-76 on the library kernels: four row-sparse tables, GMF branch folded into the
+    gather+dot kernel (pred_mf = <w_mf * mf_u[b], mf_i[id]>), MLP tower on the fp32 SGEMM."""
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument("--emb_size", type=int, default=64, help="Size of embedding vectors.")
+        parser.add_argument("--layers", type=str, default="[64]", help="Size of each layer.")
+        parser.add_argument("--table_mode", type=str, default="dense",
+                            help="embedding gradient form: dense | sparse | fused (see rechorus_b200.ops)")
+        return parser
+
+    def _neumf_init(self, args, corpus):
+        import ast
+        self.emb_size = args.emb_size
+        if self.emb_size % 4 != 0:
+            raise ValueError("rechorus_b200 kernels need emb_size % 4 == 0")
+        self.layers = list(ast.literal_eval(args.layers))      # the reference eval()s this string (NeuMF.py:38)
+        self._define_params()
+        self.apply(self.init_weights)
+        self._register_tables(self.mf_u_embeddings.weight, self.mf_i_embeddings.weight,
+                              self.mlp_u_embeddings.weight, self.mlp_i_embeddings.weight,
+                              mode=getattr(args, "table_mode", "dense"))
+
+    def _define_params(self):
+        # same module names as NeuMF.py:42-54 -> identical state_dict keys
+        d = self.emb_size
+        self.mf_u_embeddings = nn.Embedding(self.user_num, d)
+        self.mf_i_embeddings = nn.Embedding(self.item_num, d)
+        self.mlp_u_embeddings = nn.Embedding(self.user_num, d)
+        self.mlp_i_embeddings = nn.Embedding(self.item_num, d)
+        self.mlp = nn.ModuleList([])
+        pre = 2 * d
+        for width in self.layers:
+            self.mlp.append(nn.Linear(pre, width))
+            pre = width
+        self.dropout_layer = nn.Dropout(p=self.dropout)
+        self.prediction = nn.Linear(pre + d, 1, bias=False)
+
+    def forward(self, feed_dict):
+        self.check_list = []
+        u_ids = feed_dict["user_id"]        # [B]
+        i_ids = feed_dict["item_id"]        # [B, C]
+        B, C = i_ids.shape
+        d = self.emb_size
+        w_out = self.prediction.weight      # [1, d + last]: GMF part first, MLP part second (NeuMF.py:74)
+        # GMF branch: sum_k w[k] * mf_u[b,k] * mf_i[id,k]  == rowdot(w * mf_u[b], mf_i[id])
+        mf_u = ops.embedding(self.mf_u_embeddings.weight, u_ids)
+        pred = ops.score(ops.colscale(mf_u, w_out[0, :d]), self.mf_i_embeddings.weight, i_ids)
+        # MLP tower on [mlp_u[b] ; mlp_i[id]]
+        h = ops.gather_concat(self.mlp_u_embeddings.weight, self.mlp_i_embeddings.weight, u_ids, i_ids)
+        for layer in self.mlp:
+            h = ops.linear(h, layer.weight, layer.bias, relu=True)
+            if self.dropout > 0:
+                h = self.dropout_layer(h)
+        pred = pred + ops.linear(h, w_out[:, d:], None, relu=False).view(B, C)
+        return {"prediction": pred.view(feed_dict["batch_size"], -1)}
+
+
+class _AttentionParams(nn.Module):
+    """parameter holder named like utils/layers.py:9-28 (q/k/v Linear with bias, no output projection)"""
+
+    def __init__(self, d):
+        super().__init__()
+        self.q_linear = nn.Linear(d, d)
+        self.k_linear = nn.Linear(d, d)
+        self.v_linear = nn.Linear(d, d)
+
+
+class _TransformerParams(nn.Module):
+    """parameter holder named like utils/layers.py:92-110 (post-LN block with d_ff = d)"""
+
+    def __init__(self, d, d_ff):
+        super().__init__()
+        self.masked_attn_head = _AttentionParams(d)
+        self.layer_norm1 = nn.LayerNorm(d)
+        self.linear1 = nn.Linear(d, d_ff)
+        self.linear2 = nn.Linear(d_ff, d)
+        self.layer_norm2 = nn.LayerNorm(d)
+
+
+class SASRecKernels(_KernelModelMixin):
+    """models/sequential/SASRec.py:21-86 (SASRecBase) + utils/layers.py:34-63,112-118 on the library kernels."""
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument("--emb_size", type=int, default=64, help="Size of embedding vectors.")
+        parser.add_argument("--num_layers", type=int, default=1, help="Number of self-attention layers.")
+        parser.add_argument("--num_heads", type=int, default=4, help="Number of attention heads.")
+        parser.add_argument("--table_mode", type=str, default="dense",
+                            help="embedding gradient form: dense | sparse | fused (see rechorus_b200.ops)")
+        return parser
+
+    def _base_init(self, args, corpus):
+        self.emb_size = args.emb_size
+        self.max_his = args.history_max
+        self.num_layers = args.num_layers
+        self.num_heads = args.num_heads
+        if self.emb_size % 4 != 0 or self.emb_size % self.num_heads != 0:
+            raise ValueError("rechorus_b200 kernels need emb_size % 4 == 0 and emb_size % num_heads == 0")
+        self._base_define_params()
+        self.apply(self.init_weights)
+        self._register_tables(self.i_embeddings.weight, mode=getattr(args, "table_mode", "dense"))
+
+    def _base_define_params(self):
+        # same module names as SASRec.py:41-49 -> identical state_dict keys
+        self.i_embeddings = nn.Embedding(self.item_num, self.emb_size)
+        self.p_embeddings = nn.Embedding(self.max_his + 1, self.emb_size)
+        self.transformer_block = nn.ModuleList(
+            [_TransformerParams(self.emb_size, self.emb_size) for _ in range(self.num_layers)])
+
+    def user_state(self, history, lengths):
+        x = ops.embed_history(self.i_embeddings.weight, self.p_embeddings.weight, history, lengths)   # [B, L, d]
+        p = self.dropout
+        for blk in self.transformer_block:
+            a = blk.masked_attn_head
+            q = ops.linear(x, a.q_linear.weight, a.q_linear.bias)
+            k = ops.linear(x, a.k_linear.weight, a.k_linear.bias)
+            v = ops.linear(x, a.v_linear.weight, a.v_linear.bias)
+            ctx = ops.causal_attention(q, k, v, self.num_heads)
+            if p > 0:
+                ctx = torch.nn.functional.dropout(ctx, p, self.training)
+            c = ops.add_layernorm(ctx, x, blk.layer_norm1.weight, blk.layer_norm1.bias)
+            o = ops.linear(ops.linear(c, blk.linear1.weight, blk.linear1.bias, relu=True),
+                           blk.linear2.weight, blk.linear2.bias)
+            if p > 0:
+                o = torch.nn.functional.dropout(o, p, self.training)
+            x = ops.add_layernorm(o, c, blk.layer_norm2.weight, blk.layer_norm2.bias)
+        return ops.select_last(x, history, lengths)                                                    # [B, d]
+
+    def forward(self, feed_dict):
+        self.check_list = []
+        i_ids = feed_dict["item_id"]            # [B, C]
+        history = feed_dict["history_items"]    # [B, Lb] right-padded with 0
+        lengths = feed_dict["lengths"]          # [B]
+        h = self.user_state(history, lengths)
+        pred = ops.score(h, self.i_embeddings.weight, i_ids)
+        return {"prediction": pred.view(history.shape[0], -1)}
+
+
 # ======================================================================================================
 # stand-alone hosts mirroring models/BaseModel.py (used when the reference checkout is absent)
 # ======================================================================================================
@@ -301,4 +441,34 @@ class BPRMF(BPRMFKernels, GeneralModel):
 
     def __init__(self, args, corpus):
         GeneralModel.__init__(self, args, corpus)
+        self._base_init(args, corpus)
+
+
+class NeuMF(NeuMFKernels, GeneralModel):
+    """Drop-in for models/general/NeuMF.py:22-76."""
+    reader, runner = "BaseReader", "BaseRunner"
+    extra_log_args = ["emb_size", "layers"]
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser = NeuMFKernels.parse_model_args(parser)
+        return GeneralModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        GeneralModel.__init__(self, args, corpus)
+        self._neumf_init(args, corpus)
+
+
+class SASRec(SASRecKernels, SequentialModel):
+    """Drop-in for models/sequential/SASRec.py:89-105."""
+    reader, runner = "SeqReader", "BaseRunner"
+    extra_log_args = ["emb_size", "num_layers", "num_heads"]
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser = SASRecKernels.parse_model_args(parser)
+        return SequentialModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        SequentialModel.__init__(self, args, corpus)
         self._base_init(args, corpus)
