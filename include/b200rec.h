@@ -216,12 +216,26 @@ B2R_API int b2r_colscale(const float* a, const float* w, float* out, int64_t row
 B2R_API int b2r_colsum_prod(const float* a, const float* b, float* out, int64_t rows, int d, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * One whole BPRMF training step enqueued from C (no Python between kernels):
- *   gather u = U[uid] -> scores -> BPR loss + grad -> dQ -> row-sparse fused optimizer on I and on U.
+ * Fused BPRMF forward + loss + query-side backward: every candidate row is read from HBM once and stays in
+ * registers between scoring and the gradient.  Outputs: grad_pred [B,C] (= d loss / d pred, loss = mean of the
+ * per-sample losses), row_loss [B] (per-sample -log S), dQ [B,d] (= sum_c g[b,c] I[iid[b,c]]), pred [B,C]
+ * optional (NULL to skip).  Returns B2R_E_UNSUPPORTED when no fused variant exists for (d, C) -- callers then
+ * use b2r_rowdot_fwd / b2r_bpr_loss / b2r_rowdot_bwd_query.  Replaces BPRMF.py:39-42, BaseModel.py:182-185
+ * and their autograd (BaseRunner.py:205) in one kernel.
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64_t n_users, const float* I,
+                            const int64_t* iid, int64_t n_items, float* pred, float* grad_pred, float* row_loss,
+                            float* dQ, int B, int C, int d, int32_t* err_flag, b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * One whole BPRMF training step enqueued from C (no Python between kernels) on a step context:
+ *   fused gather/score/loss/dQ -> row-sparse fused optimizer on I, then on U (lazy rule, see b2r_optim).
  * Replaces one iteration of the hot loop helpers/BaseRunner.py:193-206 for models/general/BPRMF.py (the
  * per-row candidate shuffle of :187-191 is a mathematical no-op for this model and is not performed).
- * The index plans are built on a library-owned side stream so the sort overlaps the gather kernels.
- * Tables are updated in place with the lazy row-sparse rule documented at b2r_optim.
+ * The context owns a side stream on which the index plans (sorts) are built; passing the NEXT batch's ids
+ * (next_uid/next_iid, device pointers that must stay unmodified until the next call) lets the sort of step
+ * t+1 overlap the HBM-bound kernels of step t, like a data loader's prefetch.  Pass NULLs to disable.
+ * The workspace (b2r_bprmf_step_workspace_bytes) is caller-owned and must outlive the context.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
     float*  U;  float* I;            /* [n_users, d], [n_items, d]                       */
@@ -232,9 +246,12 @@ typedef struct {
 } b2r_bprmf_tables;
 
 B2R_API size_t b2r_bprmf_step_workspace_bytes(int B, int C, int d, int64_t n_users, int64_t n_items);
-B2R_API int b2r_bprmf_train_step(const b2r_bprmf_tables* t, const int64_t* uid, const int64_t* iid, int B, int C,
-                         const b2r_optim* opt, float* loss_out, void* ws, size_t ws_bytes,
-                         int32_t* err_flag, b2r_stream_t stream);
+B2R_API int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t n_users, int64_t n_items, void* ws,
+                         size_t ws_bytes);
+B2R_API int b2r_bprmf_ctx_destroy(void* ctx);
+B2R_API int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const int64_t* uid, const int64_t* iid,
+                         const int64_t* next_uid, const int64_t* next_iid, const b2r_optim* opt,
+                         float* loss_out, int32_t* err_flag, b2r_stream_t stream);
 
 #ifdef __cplusplus
 }

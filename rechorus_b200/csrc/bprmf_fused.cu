@@ -1,0 +1,188 @@
+// bprmf_fused.cu -- K1+K2a in one pass: gather the user row and the (1+K) candidate rows, score them, evaluate
+// the BPR loss and its closed-form gradient, and reduce dQ = sum_c g_c * I[id_c] -- with every candidate row
+// read from HBM exactly once and kept in registers between the scoring and the gradient phase.
+//
+// Work decomposition: a sample is owned by GPS lane groups (GPS a power of two <= groups per CTA); group j takes
+// candidates c = j, j+GPS, j+2*GPS ... (at most RPG of them, all loaded before the first reduction -> RPG
+// independent 128-bit loads in flight per lane).  Scores meet in shared memory, every group then derives the
+// softmax/sigmoid statistics of its sample redundantly (C <= 256 values, cheaper than another barrier),
+// computes g for its own rows, accumulates g*row in registers, and the GPS partial dQ vectors are summed in
+// group order (deterministic).  replaces: BPRMF.py:39-42 forward, BaseModel.py:182-185 loss, and the
+// mul/sum + loss half of loss.backward() (BaseRunner.py:205).
+#include "common.cuh"
+
+namespace b2r {
+
+__device__ __forceinline__ float sigmoidf_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int LPR>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(B2R_FULL_MASK, v, o));
+    return v;
+}
+
+template <int LPR, int RPG>
+__global__ void __launch_bounds__(256)
+k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int64_t n_users,
+              const float* __restrict__ T, const int64_t* __restrict__ ids, int64_t n_t,
+              float* __restrict__ pred, float* __restrict__ gout, float* __restrict__ row_loss,
+              float* __restrict__ dQ, int B, int C, int GPS, int32_t* err_flag) {
+    static_assert(RPG <= LPR, "ids of a group's rows are loaded one per lane");
+    constexpr int D = LPR * 4;
+    constexpr int GPC = 256 / LPR;
+    __shared__ float sp[GPC * RPG];          // scores of the samples this CTA holds (C <= GPS*RPG each)
+    __shared__ float4 part[GPC][LPR];        // partial dQ per group
+    const int sub = threadIdx.x % LPR;
+    const int grp = threadIdx.x / LPR;
+    const int SPB = GPC / GPS;
+    const int j = grp % GPS;
+    const int slot = grp / GPS;
+    float* myp = sp + slot * (GPS * RPG);
+    const float invB = 1.f / (float)B;
+    for (int64_t sbase = (int64_t)blockIdx.x * SPB; sbase < B; sbase += (int64_t)gridDim.x * SPB) {
+        const int64_t b = sbase + slot;
+        const bool have = b < B;
+        const int c_mine = j + GPS * sub;                       // the candidate lane `sub` speaks for
+        const bool mine_ok = have && sub < RPG && c_mine < C;
+
+        int64_t qrow = 0;
+        if (have) qrow = checked_id(uid[b], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
+        const float4 q = ld4(U + qrow * D + sub * 4);
+        int64_t my_id = 0;
+        if (mine_ok) my_id = checked_id(ids[b * C + c_mine], n_t, err_flag);
+
+        float4 r[RPG];
+#pragma unroll
+        for (int k = 0; k < RPG; ++k) {
+            const int64_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
+            const bool ok = have && (j + GPS * k) < C;
+            r[k] = ok ? ld_row4(T + id_k * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float mine = 0.f;
+#pragma unroll
+        for (int k = 0; k < RPG; ++k) {
+            const float s = group_sum<LPR>(dot4(q, r[k]));
+            if (sub == k) mine = s;
+        }
+        if (mine_ok) {
+            myp[c_mine] = mine;
+            if (pred != nullptr) pred[b * C + c_mine] = mine;
+        }
+        __syncthreads();
+
+        // loss statistics of this sample (every group of the sample computes them redundantly)
+        const float p = myp[0];
+        float mx = -INFINITY;
+        for (int c = 1 + sub; c < C; c += LPR) mx = fmaxf(mx, myp[c]);
+        mx = group_max<LPR>(mx);
+        float Z = 0.f, A = 0.f, Dp = 0.f;
+        for (int c = 1 + sub; c < C; c += LPR) {
+            const float n = myp[c];
+            const float e = expf(n - mx);
+            const float s = sigmoidf_f(p - n);
+            Z += e;
+            A = fmaf(e, s, A);
+            Dp = fmaf(e * s, 1.f - s, Dp);
+        }
+        Z = group_sum<LPR>(Z);
+        A = group_sum<LPR>(A);
+        Dp = group_sum<LPR>(Dp);
+        const float S = (C > 1) ? A / Z : 0.f;
+        const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
+        const float Sc = fminf(fmaxf(S, 1e-8f), 1.f - 1e-8f);
+        const float dS = inside ? -invB / S : 0.f;
+        const float invZ = (C > 1) ? 1.f / Z : 0.f;
+        float gmine = 0.f;
+        if (mine_ok) {
+            if (c_mine == 0) {
+                gmine = dS * Dp * invZ;
+            } else {
+                const float w = expf(mine - mx) * invZ;
+                const float s = sigmoidf_f(p - mine);
+                gmine = dS * w * ((s - S) - s * (1.f - s));
+            }
+            gout[b * C + c_mine] = gmine;
+        }
+        if (have && j == 0 && sub == 0) row_loss[b] = -logf(Sc);
+
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < RPG; ++k) {
+            const float gk = __shfl_sync(B2R_FULL_MASK, gmine, k, LPR);
+            fma4(acc, gk, r[k]);
+        }
+        part[grp][sub] = acc;
+        __syncthreads();
+        if (j == 0 && have) {
+            float4 tot = part[grp][sub];
+            for (int t = 1; t < GPS; ++t) {
+                const float4 x = part[grp + t][sub];
+                tot.x += x.x; tot.y += x.y; tot.z += x.z; tot.w += x.w;
+            }
+            st4(dQ + b * D + sub * 4, tot);
+        }
+        __syncthreads();
+    }
+}
+
+static int pow2ceil(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// pick rows-per-group and groups-per-sample: smallest padding GPS*RPG - C, ties -> more rows in flight
+static bool pick_shape(int C, int GPC, int max_rpg, int* RPG, int* GPS) {
+    int best_waste = 1 << 30;
+    bool found = false;
+    for (int rpg = max_rpg; rpg >= 2; rpg >>= 1) {
+        const int gps = pow2ceil((C + rpg - 1) / rpg);
+        if (gps > GPC) continue;
+        const int waste = gps * rpg - C;
+        if (waste < best_waste) {
+            best_waste = waste;
+            *RPG = rpg;
+            *GPS = gps;
+            found = true;
+        }
+    }
+    return found;
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+// returns B2R_E_UNSUPPORTED (without touching the error string semantics) when the shape has no fused variant
+extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64_t n_users, const float* I,
+                                       const int64_t* iid, int64_t n_items, float* pred, float* grad_pred,
+                                       float* row_loss, float* dQ, int B, int C, int d, int32_t* err_flag,
+                                       b2r_stream_t stream) {
+    B2R_REQUIRE(U && uid && I && iid && grad_pred && row_loss && dQ, B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: null pointer");
+    B2R_REQUIRE(B > 0 && C > 0, B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: B=%d C=%d", B, C);
+    B2R_REQUIRE(aligned16(U) && aligned16(I) && aligned16(dQ), B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: alignment");
+    cudaStream_t s = as_stream(stream);
+    int RPG = 0, GPS = 0;
+    const int GPC = d == 32 ? 32 : (d == 64 ? 16 : (d == 128 ? 8 : 0));
+    if (GPC == 0 || !pick_shape(C, GPC, d == 128 ? 16 : 8, &RPG, &GPS))
+        return set_error(B2R_E_UNSUPPORTED, "b2r_bprmf_fused_fwd_bwd: no fused variant for d=%d C=%d", d, C);
+    const int SPB = GPC / GPS;
+    const int64_t need = ((int64_t)B + SPB - 1) / SPB;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const int grid = (int)(need < cap ? need : cap);
+#define B2R_FUSED(LPR, R)                                                                              \
+    k_bprmf_fused<LPR, R><<<grid, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, \
+                                               GPS, err_flag)
+    if (d == 32) {
+        if (RPG == 2) B2R_FUSED(8, 2); else if (RPG == 4) B2R_FUSED(8, 4); else B2R_FUSED(8, 8);
+    } else if (d == 64) {
+        if (RPG == 2) B2R_FUSED(16, 2); else if (RPG == 4) B2R_FUSED(16, 4); else B2R_FUSED(16, 8);
+    } else {
+        if (RPG == 2) B2R_FUSED(32, 2); else if (RPG == 4) B2R_FUSED(32, 4);
+        else if (RPG == 8) B2R_FUSED(32, 8); else B2R_FUSED(32, 16);
+    }
+#undef B2R_FUSED
+    B2R_LAUNCH_OK("k_bprmf_fused");
+    return 0;
+}

@@ -1,17 +1,28 @@
-// bprmf_step.cu -- one whole BPRMF training step enqueued from C (b2r_bprmf_train_step).
+// bprmf_step.cu -- one whole BPRMF training step enqueued from C (b2r_bprmf_train_step) on a step context.
 //
-// Stream plan:   main :  gather u -> rowdot fwd -> loss+grad -> dQ ------------> segment(I) -> segment(U)
-//                side :  plan(item ids) -> plan(user ids) ----------------------^ (event join)
-// The sort only depends on the ids, so it runs beside the HBM-bound gather kernels on a library-owned
-// non-blocking stream; the join is an event wait, never a host synchronisation.
+// Stream plan (step t):
+//   main :  fused gather+score+loss+dQ (rows read once) -> mean(loss) -> [wait plan(t)] -> segment+opt(I) -> segment+opt(U)
+//   side :  plan(t+1) for the NEXT batch's ids (or plan(t) itself when nothing was prefetched)
+// The index plan (radix sort of the ids) only depends on the ids, so the context builds it one step ahead on
+// a library-owned non-blocking stream while the HBM-bound kernels of the current step run; joins are event
+// waits, never host synchronisations.  Plans are double-buffered in the caller-provided workspace.
 #include "common.cuh"
+
+extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64_t n_users, const float* I,
+                                       const int64_t* iid, int64_t n_items, float* pred, float* grad_pred,
+                                       float* row_loss, float* dQ, int B, int C, int d, int32_t* err_flag,
+                                       b2r_stream_t stream);
 
 namespace b2r {
 
+struct PlanBuf {
+    size_t ik, ip, is, inu, uk, up, us, unu;
+};
+
 struct StepLayout {
     size_t q, pred, g, rows, dQ;
-    size_t ik, ip, is, inu, iws, iws_bytes;
-    size_t uk, up, us, unu, uws, uws_bytes;
+    PlanBuf plan[2];
+    size_t iws, iws_bytes, uws, uws_bytes;
     size_t total;
 };
 
@@ -28,44 +39,36 @@ static bool step_layout(int B, int C, int d, int64_t n_users, int64_t n_items, S
     L->g = take(n * 4);
     L->rows = take((size_t)B * 4);
     L->dQ = take((size_t)B * d * 4);
-    L->ik = take(n * 4);
-    L->ip = take(n * 4);
-    L->is = take(n * 4);
-    L->inu = take(4);
+    for (int s = 0; s < 2; ++s) {
+        L->plan[s].ik = take(n * 4);
+        L->plan[s].ip = take(n * 4);
+        L->plan[s].is = take(n * 4);
+        L->plan[s].inu = take(4);
+        L->plan[s].uk = take((size_t)B * 4);
+        L->plan[s].up = take((size_t)B * 4);
+        L->plan[s].us = take((size_t)B * 4);
+        L->plan[s].unu = take(4);
+    }
     L->iws_bytes = b2r_plan_workspace_bytes((int64_t)n, n_items);
     L->iws = take(L->iws_bytes);
-    L->uk = take((size_t)B * 4);
-    L->up = take((size_t)B * 4);
-    L->us = take((size_t)B * 4);
-    L->unu = take(4);
     L->uws_bytes = b2r_plan_workspace_bytes(B, n_users);
     L->uws = take(L->uws_bytes);
     L->total = off;
     return L->iws_bytes != 0 && L->uws_bytes != 0;
 }
 
-struct SideStream {
-    int dev = -1;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+struct StepCtx {
+    int B, C, d;
+    int64_t n_users, n_items;
+    StepLayout L;
+    char* ws;
+    cudaStream_t side;
+    cudaEvent_t fork, join[2];
+    int slot;                         // plan buffer the NEXT step will read if it was prefetched
+    const void* pre_uid;
+    const void* pre_iid;
+    bool have_pre;
 };
-
-// one side stream + event pair per device, created on first use and kept for the process lifetime
-static int side_stream(SideStream** out) {
-    static SideStream cache[16];
-    int dev = 0;
-    B2R_CUDA_OK(cudaGetDevice(&dev));
-    B2R_REQUIRE(dev >= 0 && dev < 16, B2R_E_UNSUPPORTED, "device index %d out of range", dev);
-    SideStream& s = cache[dev];
-    if (s.dev != dev) {
-        B2R_CUDA_OK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        B2R_CUDA_OK(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
-        B2R_CUDA_OK(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
-        s.dev = dev;
-    }
-    *out = &s;
-    return 0;
-}
 
 }  // namespace b2r
 
@@ -78,78 +81,152 @@ extern "C" size_t b2r_bprmf_step_workspace_bytes(int B, int C, int d, int64_t n_
     return L.total;
 }
 
-extern "C" int b2r_bprmf_train_step(const b2r_bprmf_tables* t, const int64_t* uid, const int64_t* iid, int B,
-                                    int C, const b2r_optim* opt, float* loss_out, void* ws, size_t ws_bytes,
-                                    int32_t* err_flag, b2r_stream_t stream) {
-    B2R_REQUIRE(t && uid && iid && opt && loss_out && ws, B2R_E_BADARG, "b2r_bprmf_train_step: null pointer");
-    B2R_REQUIRE(B > 0 && C > 0, B2R_E_BADARG, "b2r_bprmf_train_step: B=%d C=%d", B, C);
-    const int d = t->d;
-    StepLayout L;
-    B2R_REQUIRE(step_layout(B, C, d, t->n_users, t->n_items, &L), B2R_E_UNSUPPORTED,
-                "b2r_bprmf_train_step: cannot size the index plans");
-    B2R_REQUIRE(ws_bytes >= L.total, B2R_E_WORKSPACE, "b2r_bprmf_train_step: workspace %zu < required %zu",
-                ws_bytes, L.total);
+extern "C" int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t n_users, int64_t n_items, void* ws,
+                                    size_t ws_bytes) {
+    B2R_REQUIRE(ctx_out && ws, B2R_E_BADARG, "b2r_bprmf_ctx_create: null pointer");
+    B2R_REQUIRE(B > 0 && C > 0 && d > 0 && d % 4 == 0, B2R_E_BADARG, "b2r_bprmf_ctx_create: B=%d C=%d d=%d", B, C, d);
     B2R_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, B2R_E_BADARG, "workspace must be 256-byte aligned");
-    char* base = static_cast<char*>(ws);
-    float* q = reinterpret_cast<float*>(base + L.q);
-    float* pred = reinterpret_cast<float*>(base + L.pred);
-    float* g = reinterpret_cast<float*>(base + L.g);
-    float* rows = reinterpret_cast<float*>(base + L.rows);
-    float* dQ = reinterpret_cast<float*>(base + L.dQ);
-    uint32_t* ik = reinterpret_cast<uint32_t*>(base + L.ik);
-    uint32_t* ip = reinterpret_cast<uint32_t*>(base + L.ip);
-    int32_t* is = reinterpret_cast<int32_t*>(base + L.is);
-    int32_t* inu = reinterpret_cast<int32_t*>(base + L.inu);
-    uint32_t* uk = reinterpret_cast<uint32_t*>(base + L.uk);
-    uint32_t* up = reinterpret_cast<uint32_t*>(base + L.up);
-    int32_t* us = reinterpret_cast<int32_t*>(base + L.us);
-    int32_t* unu = reinterpret_cast<int32_t*>(base + L.unu);
+    StepCtx* c = new StepCtx();
+    c->B = B; c->C = C; c->d = d; c->n_users = n_users; c->n_items = n_items;
+    if (!step_layout(B, C, d, n_users, n_items, &c->L)) {
+        delete c;
+        return set_error(B2R_E_UNSUPPORTED, "b2r_bprmf_ctx_create: cannot size the index plans");
+    }
+    if (ws_bytes < c->L.total) {
+        const size_t need = c->L.total;
+        delete c;
+        return set_error(B2R_E_WORKSPACE, "b2r_bprmf_ctx_create: workspace %zu < required %zu", ws_bytes, need);
+    }
+    c->ws = static_cast<char*>(ws);
+    c->slot = 0;
+    c->have_pre = false;
+    c->pre_uid = c->pre_iid = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[1], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete c;
+        return set_error((int)e, "b2r_bprmf_ctx_create: %s", cudaGetErrorString(e));
+    }
+    *ctx_out = c;
+    return 0;
+}
 
+extern "C" int b2r_bprmf_ctx_destroy(void* ctx) {
+    if (!ctx) return 0;
+    StepCtx* c = static_cast<StepCtx*>(ctx);
+    cudaStreamSynchronize(c->side);
+    cudaStreamDestroy(c->side);
+    cudaEventDestroy(c->fork);
+    cudaEventDestroy(c->join[0]);
+    cudaEventDestroy(c->join[1]);
+    delete c;
+    return 0;
+}
+
+static int build_plans(StepCtx* c, int slot, const int64_t* uid, const int64_t* iid, int32_t* err_flag) {
+    char* base = c->ws;
+    const PlanBuf& p = c->L.plan[slot];
+    const int64_t n = (int64_t)c->B * c->C;
+    profile_begin(B2R_PROF_PLAN_I, c->side);
+    int rc = b2r_plan_build(iid, n, c->n_items, reinterpret_cast<uint32_t*>(base + p.ik),
+                            reinterpret_cast<uint32_t*>(base + p.ip), reinterpret_cast<int32_t*>(base + p.is),
+                            reinterpret_cast<int32_t*>(base + p.inu), base + c->L.iws, c->L.iws_bytes, err_flag, c->side);
+    if (rc != 0) return rc;
+    profile_end(B2R_PROF_PLAN_I, c->side);
+    rc = b2r_plan_build(uid, c->B, c->n_users, reinterpret_cast<uint32_t*>(base + p.uk),
+                        reinterpret_cast<uint32_t*>(base + p.up), reinterpret_cast<int32_t*>(base + p.us),
+                        reinterpret_cast<int32_t*>(base + p.unu), base + c->L.uws, c->L.uws_bytes, err_flag, c->side);
+    if (rc != 0) return rc;
+    B2R_CUDA_OK(cudaEventRecord(c->join[slot], c->side));
+    return 0;
+}
+
+extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const int64_t* uid, const int64_t* iid,
+                                    const int64_t* next_uid, const int64_t* next_iid, const b2r_optim* opt,
+                                    float* loss_out, int32_t* err_flag, b2r_stream_t stream) {
+    B2R_REQUIRE(ctx && t && uid && iid && opt && loss_out, B2R_E_BADARG, "b2r_bprmf_train_step: null pointer");
+    StepCtx* c = static_cast<StepCtx*>(ctx);
+    B2R_REQUIRE(t->d == c->d && t->n_users == c->n_users && t->n_items == c->n_items, B2R_E_BADARG,
+                "b2r_bprmf_train_step: tables do not match the context");
+    const int B = c->B, C = c->C, d = c->d;
+    char* base = c->ws;
+    float* pred = reinterpret_cast<float*>(base + c->L.pred);
+    float* g = reinterpret_cast<float*>(base + c->L.g);
+    float* rows = reinterpret_cast<float*>(base + c->L.rows);
+    float* dQ = reinterpret_cast<float*>(base + c->L.dQ);
     cudaStream_t main_s = as_stream(stream);
-    SideStream* side = nullptr;
-    int rc = side_stream(&side);
-    if (rc != 0) return rc;
     const int64_t n = (int64_t)B * C;
+    int rc;
 
-    // fork: the plans depend only on the ids
-    B2R_CUDA_OK(cudaEventRecord(side->fork, main_s));
-    B2R_CUDA_OK(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    profile_begin(B2R_PROF_PLAN_I, side->stream);
-    rc = b2r_plan_build(iid, n, t->n_items, ik, ip, is, inu, base + L.iws, L.iws_bytes, err_flag, side->stream);
-    if (rc != 0) return rc;
-    profile_end(B2R_PROF_PLAN_I, side->stream);
-    rc = b2r_plan_build(uid, B, t->n_users, uk, up, us, unu, base + L.uws, L.uws_bytes, err_flag, side->stream);
-    if (rc != 0) return rc;
-    B2R_CUDA_OK(cudaEventRecord(side->join, side->stream));
+    // everything the side stream does from here on is ordered after what main has enqueued so far
+    // (in particular after the previous step's readers of the plan buffer about to be overwritten)
+    B2R_CUDA_OK(cudaEventRecord(c->fork, main_s));
+    B2R_CUDA_OK(cudaStreamWaitEvent(c->side, c->fork, 0));
 
-    // main: forward, loss, query-side backward
-    rc = b2r_gather_rows(t->U, uid, t->n_users, q, B, d, err_flag, main_s);
-    if (rc != 0) return rc;
+    const int cur = c->slot;
+    if (!(c->have_pre && c->pre_uid == uid && c->pre_iid == iid)) {
+        rc = build_plans(c, cur, uid, iid, err_flag);     // nothing prefetched for this batch: build it now
+        if (rc != 0) return rc;
+    }
+    if (next_uid != nullptr && next_iid != nullptr) {
+        rc = build_plans(c, cur ^ 1, next_uid, next_iid, err_flag);
+        if (rc != 0) return rc;
+        c->have_pre = true;
+        c->pre_uid = next_uid;
+        c->pre_iid = next_iid;
+    } else {
+        c->have_pre = false;
+    }
+    c->slot = cur ^ 1;
+
+    // main: forward + loss + query-side backward
     profile_begin(B2R_PROF_SCORE_FWD, main_s);
-    rc = b2r_rowdot_fwd(q, nullptr, B, t->I, iid, t->n_items, pred, B, C, d, err_flag, main_s);
-    if (rc != 0) return rc;
-    profile_end(B2R_PROF_SCORE_FWD, main_s);
-    profile_begin(B2R_PROF_LOSS, main_s);
-    rc = b2r_bpr_loss(pred, loss_out, g, rows, B, C, main_s);
-    if (rc != 0) return rc;
-    profile_end(B2R_PROF_LOSS, main_s);
-    profile_begin(B2R_PROF_SCORE_BWDQ, main_s);
-    rc = b2r_rowdot_bwd_query(g, t->I, iid, t->n_items, dQ, B, C, d, main_s);
-    if (rc != 0) return rc;
-    profile_end(B2R_PROF_SCORE_BWDQ, main_s);
+    rc = b2r_bprmf_fused_fwd_bwd(t->U, uid, t->n_users, t->I, iid, t->n_items, nullptr, g, rows, dQ, B, C, d, err_flag,
+                                 main_s);
+    const bool fused = (rc == 0);
+    if (rc != 0 && rc != B2R_E_UNSUPPORTED) return rc;
+    if (fused) profile_end(B2R_PROF_SCORE_FWD, main_s);
+    const float* item_src = t->U;           // dI = g * U[uid[b]]  (U is updated only after the item table)
+    const int64_t* item_src_id = uid;
+    if (fused) {
+        rc = launch_mean_rows(rows, loss_out, B, main_s);
+        if (rc != 0) return rc;
+    } else {
+        float* q = reinterpret_cast<float*>(base + c->L.q);
+        rc = b2r_gather_rows(t->U, uid, t->n_users, q, B, d, err_flag, main_s);
+        if (rc != 0) return rc;
+        rc = b2r_rowdot_fwd(q, nullptr, B, t->I, iid, t->n_items, pred, B, C, d, err_flag, main_s);
+        if (rc != 0) return rc;
+        profile_end(B2R_PROF_SCORE_FWD, main_s);
+        profile_begin(B2R_PROF_LOSS, main_s);
+        rc = b2r_bpr_loss(pred, loss_out, g, rows, B, C, main_s);
+        if (rc != 0) return rc;
+        profile_end(B2R_PROF_LOSS, main_s);
+        profile_begin(B2R_PROF_SCORE_BWDQ, main_s);
+        rc = b2r_rowdot_bwd_query(g, t->I, iid, t->n_items, dQ, B, C, d, main_s);
+        if (rc != 0) return rc;
+        profile_end(B2R_PROF_SCORE_BWDQ, main_s);
+        item_src = q;
+        item_src_id = nullptr;
+    }
 
-    // join, then the fused backward+optimizer on each table (item table first; it only reads the q snapshot)
-    B2R_CUDA_OK(cudaStreamWaitEvent(main_s, side->join, 0));
-    b2r_grad_source si{q, g, nullptr, n, C, 0 /* ld = d */};
+    // join plan(t), then the fused backward+optimizer on each table (item table first: it reads U rows)
+    B2R_CUDA_OK(cudaStreamWaitEvent(main_s, c->join[cur], 0));
+    const PlanBuf& p = c->L.plan[cur];
+    b2r_grad_source si{item_src, g, item_src_id, n, C, 0};
     profile_begin(B2R_PROF_SEGMENT_I, main_s);
-    rc = b2r_segment_apply(ik, ip, is, inu, n, t->n_items, d, &si, nullptr, 2, nullptr, nullptr, nullptr, t->I, t->Im, t->Iv,
-                           opt, main_s);
+    rc = b2r_segment_apply(reinterpret_cast<uint32_t*>(base + p.ik), reinterpret_cast<uint32_t*>(base + p.ip),
+                           reinterpret_cast<int32_t*>(base + p.is), reinterpret_cast<int32_t*>(base + p.inu), n,
+                           t->n_items, d, &si, nullptr, 2, nullptr, nullptr, nullptr, t->I, t->Im, t->Iv, opt, main_s);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_SEGMENT_I, main_s);
     b2r_grad_source su{dQ, nullptr, nullptr, B, 1, 0};
     profile_begin(B2R_PROF_SEGMENT_U, main_s);
-    rc = b2r_segment_apply(uk, up, us, unu, B, t->n_users, d, &su, nullptr, 2, nullptr, nullptr, nullptr, t->U, t->Um, t->Uv,
-                           opt, main_s);
+    rc = b2r_segment_apply(reinterpret_cast<uint32_t*>(base + p.uk), reinterpret_cast<uint32_t*>(base + p.up),
+                           reinterpret_cast<int32_t*>(base + p.us), reinterpret_cast<int32_t*>(base + p.unu), B,
+                           t->n_users, d, &su, nullptr, 2, nullptr, nullptr, nullptr, t->U, t->Um, t->Uv, opt, main_s);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_SEGMENT_U, main_s);
     return 0;

@@ -43,6 +43,9 @@ void count_launch();
 void profile_begin(int tag, cudaStream_t s);
 void profile_end(int tag, cudaStream_t s);
 
+// fixed-order mean of B per-sample losses (loss.cu)
+int launch_mean_rows(const float* row_loss, float* out, int B, cudaStream_t s);
+
 static inline cudaStream_t as_stream(b2r_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -69,6 +69,12 @@ k_mean_rows(const float* __restrict__ row_loss, float* __restrict__ out, int B) 
     if (threadIdx.x == 0) out[0] = sm[0] / (float)B;
 }
 
+int launch_mean_rows(const float* row_loss, float* out, int B, cudaStream_t s) {
+    k_mean_rows<<<1, 1024, 0, s>>>(row_loss, out, B);
+    B2R_LAUNCH_OK("k_mean_rows");
+    return 0;
+}
+
 }  // namespace b2r
 
 using namespace b2r;
@@ -80,7 +86,5 @@ extern "C" int b2r_bpr_loss(const float* pred, float* loss_out, float* grad_pred
     cudaStream_t s = as_stream(stream);
     k_bpr_loss_rows<<<(B + 7) / 8, 256, 0, s>>>(pred, grad_pred, row_ws, B, C);
     B2R_LAUNCH_OK("k_bpr_loss_rows");
-    k_mean_rows<<<1, 1024, 0, s>>>(row_ws, loss_out, B);
-    B2R_LAUNCH_OK("k_mean_rows");
-    return 0;
+    return launch_mean_rows(row_ws, loss_out, B, s);
 }

@@ -7,6 +7,8 @@
 // (mode 2: the weight/moment rows are requested before the walk so their HBM latency overlaps it).
 // HBM-bound: per unique row 1 write (mode 0) or 3 reads + 3 writes of 4d bytes (Adam); contribution
 // operands (user rows, grad_pred) are a few MB and stay in L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2r {
@@ -99,6 +101,85 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
             st4(W + row * D + sub * 4, w);
             if (opt.kind == 1) st4(M + row * D + sub * 4, m);
             if (opt.kind != 0) st4(V + row * D + sub * 4, v);
+        }
+    }
+}
+
+// Fused backward+optimizer (mode 2) with RPI unique rows per lane group in flight: the dependent-load chain
+// (segment bounds -> row id -> weight/moment rows, and position -> coefficient/source row) is walked for RPI
+// rows at once, so RPI x (3 row loads + 1 source row load) are outstanding per lane instead of 4.  Consecutive
+// unique rows are adjacent in the sorted order, i.e. ascending addresses a few rows apart in W/m/v.
+template <int LPR, int RPI>
+__global__ void __launch_bounds__(256)
+k_segment_optim(const uint32_t* __restrict__ sorted_key, const uint32_t* __restrict__ sorted_pos,
+                const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n, int64_t n_rows,
+                Src s0, Src s1, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, b2r_optim opt) {
+    static_assert(RPI < LPR, "segment bounds are loaded one per lane");
+    constexpr int D = LPR * 4;
+    constexpr int GPC = 256 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = threadIdx.x % LPR;
+    const int grp = threadIdx.x / LPR;
+    // shuffles below run inside loops whose trip count differs between the lane groups of a warp
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane - sub));
+    const int nu = *n_uniq;
+    for (int u0 = (blockIdx.x * GPC + grp) * RPI; u0 < nu; u0 += gridDim.x * GPC * RPI) {
+        // lane k <= RPI holds seg_start[u0 + k] (n past the end); lane k < RPI then its row id and length
+        int sv = n;
+        if (sub <= RPI && u0 + sub < nu) sv = seg_start[u0 + sub];
+        const int nxt = __shfl_sync(gmask, sv, (sub + 1) % LPR, LPR);
+        int64_t myrow = n_rows;            // sentinel = skip
+        int mylen = 0;
+        if (sub < RPI && u0 + sub < nu) {
+            myrow = sorted_key[sv];
+            mylen = nxt - sv;
+            if (myrow >= n_rows) mylen = 0;
+        }
+        int64_t row[RPI];
+        float4 w[RPI], m[RPI], v[RPI], acc[RPI];
+        int maxlen = 0;
+#pragma unroll
+        for (int k = 0; k < RPI; ++k) {
+            row[k] = __shfl_sync(gmask, myrow, k, LPR);
+            maxlen = max(maxlen, __shfl_sync(gmask, mylen, k, LPR));
+            acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row[k] < n_rows) {
+                w[k] = ld4(W + row[k] * D + sub * 4);
+                if (opt.kind == 1) m[k] = ld4(M + row[k] * D + sub * 4);
+                if (opt.kind != 0) v[k] = ld4(V + row[k] * D + sub * 4);
+            }
+        }
+        // contributions, t-th of every row in parallel (ascending position within a row -> deterministic)
+        for (int t = 0; t < maxlen; ++t) {
+            int64_t r = 0;
+            float c = 0.f;
+            int which = 0;
+            if (sub < RPI && t < mylen) {
+                const uint32_t p = sorted_pos[sv + t];
+                contribution(s0, s1, p, r, c);
+                which = ((int64_t)p < s0.n) ? 0 : 1;
+            }
+#pragma unroll
+            for (int k = 0; k < RPI; ++k) {
+                const int64_t rk = __shfl_sync(gmask, r, k, LPR);
+                const float ck = __shfl_sync(gmask, c, k, LPR);
+                const int wk = __shfl_sync(gmask, which, k, LPR);
+                const int lk = __shfl_sync(gmask, mylen, k, LPR);
+                if (t < lk) {
+                    const float* base = wk ? s1.src : s0.src;
+                    const int ld = wk ? s1.ld : s0.ld;
+                    fma4(acc[k], ck, ld4(base + rk * ld + sub * 4));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RPI; ++k) {
+            if (row[k] < n_rows) {
+                optim_update(opt, w[k], m[k], v[k], acc[k]);
+                st4(W + row[k] * D + sub * 4, w[k]);
+                if (opt.kind == 1) st4(M + row[k] * D + sub * 4, m[k]);
+                if (opt.kind != 0) st4(V + row[k] * D + sub * 4, v[k]);
+            }
         }
     }
 }
@@ -267,9 +348,33 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
                                                                a, b, uniq_rows, grad_rows, dense, W, m, v, o); \
         }                                                                                              \
     } while (0)
+    static int rpi = -1;                 // tuning knob (B2R_SEG_RPI = 0 | 1 | 2 | 4), read once; 0 = one-row kernel
+    if (rpi < 0) {
+        const char* e = getenv("B2R_SEG_RPI");
+        rpi = e ? atoi(e) : 4;
+        if (rpi != 0 && rpi != 1 && rpi != 2 && rpi != 4) rpi = 4;
+    }
+#define B2R_OPT(LPR, RPI)                                                                              \
+    do {                                                                                               \
+        constexpr int GPC = 256 / LPR;                                                                 \
+        int64_t need = (n + (int64_t)GPC * RPI - 1) / ((int64_t)GPC * RPI);                            \
+        const int64_t cap = (int64_t)sm_count() * 16;                                                  \
+        const int grid = (int)(need < cap ? need : cap);                                               \
+        k_segment_optim<LPR, RPI><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, n_rows, a, b, \
+                                                       W, m, v, o);                                    \
+    } while (0)
+#define B2R_OPT_R(LPR)                                                                                 \
+    do {                                                                                               \
+        if (rpi == 1) B2R_OPT(LPR, 1); else if (rpi == 2) B2R_OPT(LPR, 2); else B2R_OPT(LPR, 4);       \
+    } while (0)
     if (mode == 0) B2R_SEG_D(0);
     else if (mode == 1) B2R_SEG_D(1);
+    else if (rpi != 0 && d == 32) B2R_OPT_R(8);
+    else if (rpi != 0 && d == 64) B2R_OPT_R(16);
+    else if (rpi != 0 && d == 128) B2R_OPT_R(32);
     else B2R_SEG_D(2);
+#undef B2R_OPT_R
+#undef B2R_OPT
 #undef B2R_SEG_D
 #undef B2R_SEG
     B2R_LAUNCH_OK("k_segment_apply");

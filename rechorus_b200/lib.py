@@ -91,10 +91,15 @@ SIGNATURES = {
                                        C.c_void_p, C.c_size_t, C.c_void_p]),
     "b2r_colscale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "b2r_colsum_prod": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "b2r_bprmf_fused_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p]),
     "b2r_bprmf_step_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64]),
-    "b2r_bprmf_train_step": (C.c_int, [C.POINTER(BprmfTables), C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                       C.POINTER(Optim), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
-                                       C.c_void_p]),
+    "b2r_bprmf_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                       C.c_void_p, C.c_size_t]),
+    "b2r_bprmf_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "b2r_bprmf_train_step": (C.c_int, [C.c_void_p, C.POINTER(BprmfTables), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.POINTER(Optim), C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -348,16 +348,58 @@ def bpr_loss(pred: torch.Tensor) -> torch.Tensor:
 # whole-step entry points (one C call per training step)
 # --------------------------------------------------------------------------------------------------
 
-_step_ws = {}
+def bprmf_fused_fwd_bwd(U, uid, I, iid):
+    """b2r_bprmf_fused_fwd_bwd -> (pred [B,C], grad_pred [B,C], row_loss [B], dQ [B,d]); raises when the shape has
+    no fused variant."""
+    _need_cuda(U, I, uid, iid)
+    U, I, uid, iid = _f32c(U, "U"), _f32c(I, "I"), _i64c(uid, "uid"), _i64c(iid, "iid")
+    B, Cn = iid.shape
+    d = U.shape[1]
+    pred = torch.empty((B, Cn), dtype=torch.float32, device=U.device)
+    gp = torch.empty((B, Cn), dtype=torch.float32, device=U.device)
+    rl = torch.empty(B, dtype=torch.float32, device=U.device)
+    dq = torch.empty((B, d), dtype=torch.float32, device=U.device)
+    L = _lib.load()
+    _lib.check(L.b2r_bprmf_fused_fwd_bwd(_p(U), _p(uid), U.shape[0], _p(I), _p(iid), I.shape[0], _p(pred), _p(gp),
+                                         _p(rl), _p(dq), B, Cn, d, _p(err_flag(U.device)), _stream()),
+               "b2r_bprmf_fused_fwd_bwd")
+    return pred, gp, rl, dq
+
+
+_step_ctx = {}
+
+
+class _StepContext:
+    """b2r_bprmf_ctx: workspace + side stream + double-buffered index plans for one (B, C, d, table sizes)."""
+
+    def __init__(self, device, B, Cn, d, n_users, n_items):
+        L = _lib.load()
+        nbytes = L.b2r_bprmf_step_workspace_bytes(B, Cn, d, n_users, n_items)
+        if nbytes == 0:
+            raise _lib.B200RecError("b2r_bprmf_step_workspace_bytes returned 0")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.handle = C.c_void_p()
+        _lib.check(L.b2r_bprmf_ctx_create(C.byref(self.handle), B, Cn, d, n_users, n_items, _p(self.ws), nbytes),
+                   "b2r_bprmf_ctx_create")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().b2r_bprmf_ctx_destroy(self.handle)
+        except Exception:
+            pass
 
 
 def bprmf_train_step(U: torch.nn.Parameter, I: torch.nn.Parameter, optimizer, uid: torch.Tensor,
-                     iid: torch.Tensor) -> torch.Tensor:
-    """b2r_bprmf_train_step: forward + BPR loss + backward + fused row-sparse optimizer, in place."""
+                     iid: torch.Tensor, next_uid: Optional[torch.Tensor] = None,
+                     next_iid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """b2r_bprmf_train_step: forward + BPR loss + backward + fused row-sparse optimizer, in place.
+    next_uid/next_iid (optional): the NEXT batch's id tensors, already on the device and left untouched until
+    the next call -- their index plan is built on the side stream while this step's kernels run."""
     from .optim import RowSparseOptimizer
     if not isinstance(optimizer, RowSparseOptimizer):
         raise _lib.B200RecError("train_step needs model.optimizer to be a rechorus_b200.optim.RowSparseOptimizer")
-    _need_cuda(U, I, uid, iid)
+    _need_cuda(U, I, uid, iid, next_uid, next_iid)
     uid, iid = _i64c(uid, "user_id"), _i64c(iid, "item_id")
     B, Cn = iid.shape
     d = U.shape[1]
@@ -365,21 +407,24 @@ def bprmf_train_step(U: torch.nn.Parameter, I: torch.nn.Parameter, optimizer, ui
     if eu["wd"] != ei["wd"]:
         raise _lib.B200RecError("fused step expects one weight decay for both tables")
     L = _lib.load()
-    key = (U.device.index, B, Cn, d, U.shape[0], I.shape[0])
-    ws = _step_ws.get(key)
-    if ws is None:
-        nbytes = L.b2r_bprmf_step_workspace_bytes(B, Cn, d, U.shape[0], I.shape[0])
-        if nbytes == 0:
-            raise _lib.B200RecError("b2r_bprmf_step_workspace_bytes returned 0")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=U.device)
-        _step_ws[key] = ws
+    key = (U.device.index, B, Cn, d, U.shape[0], I.shape[0], _stream())
+    ctx = _step_ctx.get(key)
+    if ctx is None:
+        ctx = _step_ctx[key] = _StepContext(U.device, B, Cn, d, U.shape[0], I.shape[0])
+    if next_uid is not None and next_iid is not None:
+        if tuple(next_iid.shape) != (B, Cn) or next_uid.numel() != B:
+            raise ValueError("prefetched batch must have the same shape as the current one")
+        next_uid, next_iid = _i64c(next_uid, "next user_id"), _i64c(next_iid, "next item_id")
+    else:
+        next_uid = next_iid = None
     optimizer.advance()
     opt = optimizer._opt(ei["wd"])
     tables = _lib.BprmfTables(_p(U.data), _p(I.data), _p(eu["m"]), _p(eu["v"]), _p(ei["m"]), _p(ei["v"]),
                               U.shape[0], I.shape[0], d, 0)
     loss = torch.empty((), dtype=torch.float32, device=U.device)
-    _lib.check(L.b2r_bprmf_train_step(C.byref(tables), _p(uid), _p(iid), B, Cn, C.byref(opt), _p(loss), _p(ws),
-                                      ws.numel(), _p(err_flag(U.device)), _stream()), "b2r_bprmf_train_step")
+    _lib.check(L.b2r_bprmf_train_step(ctx.handle, C.byref(tables), _p(uid), _p(iid), _p(next_uid), _p(next_iid),
+                                      C.byref(opt), _p(loss), _p(err_flag(U.device)), _stream()),
+               "b2r_bprmf_train_step")
     return loss
 
 

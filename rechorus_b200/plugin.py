@@ -91,12 +91,17 @@ class BPRMFKernels(_KernelModelMixin):
         pred = ops.score(u, self.i_embeddings.weight, i_ids)          # [B, C]   (gather + dot kernel)
         return {"prediction": pred.view(feed_dict["batch_size"], -1)}
 
-    def train_step(self, feed_dict) -> torch.Tensor:
+    def train_step(self, feed_dict, next_feed_dict=None) -> torch.Tensor:
         """One whole training step (forward, BPR loss, backward, row-sparse optimizer update) enqueued by a
         single C call (b2r_bprmf_train_step) -- the body of helpers/BaseRunner.py:193-206 for this model.
-        Needs ``self.optimizer`` to be a ``RowSparseOptimizer``.  Returns the loss as a device scalar."""
+        Needs ``self.optimizer`` to be a ``RowSparseOptimizer``.  ``next_feed_dict`` (optional) is the next
+        batch, already on the device: its index plan is prefetched while this step runs.  Returns the loss as a
+        device scalar."""
+        nu = ni = None
+        if next_feed_dict is not None:
+            nu, ni = next_feed_dict["user_id"], next_feed_dict["item_id"]
         return ops.bprmf_train_step(self.u_embeddings.weight, self.i_embeddings.weight, self.optimizer,
-                                    feed_dict["user_id"], feed_dict["item_id"])
+                                    feed_dict["user_id"], feed_dict["item_id"], nu, ni)
 
 
 class NeuMFKernels(_KernelModelMixin):
