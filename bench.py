@@ -210,7 +210,7 @@ def run_ours(args, rank, world, local_rank):
     for tag in tags.values():
         lib.b2r_profile_arm(tag, None, None)
     kern_ms = {name: statistics.mean(a.elapsed_time(b) for a, b in evs[name].values()) for name in tags}
-    fused = kern_ms["score_bwd_query"] < 0.002       # the fused kernel replaces fwd + loss + bwd_query
+    fused = kern_ms["score_bwd_query"] < 0.012       # the fused kernel replaces fwd + loss + bwd_query
     if fused:
         kern_ms["fused_score_loss_bwd"] = kern_ms.pop("score_fwd")
         kern_ms.pop("score_bwd_query")

@@ -130,6 +130,8 @@ typedef struct {
 typedef struct {
     int32_t kind;
     float   lr, beta1, beta2, eps, weight_decay, bc1, bc2;
+    int32_t state_ld;   /* row stride (floats) of the m / v arrays in the row-sparse kernels; 0 = d.  2*d lets a table
+                           keep m and v interleaved per row ([n_rows][2][d]): one 2*4d-byte burst instead of two */
 } b2r_optim;
 
 /* Segment reduce over a plan built on the concatenation of up to two sources' ids
@@ -144,6 +146,24 @@ B2R_API int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sorted
                       const b2r_grad_source* s0, const b2r_grad_source* s1,
                       int mode, int64_t* uniq_rows, float* grad_rows, float* dense,
                       float* W, float* m, float* v, const b2r_optim* opt, b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bucketed form of plan + segment for the hot path (modes 1 and 2 only; d in {32, 64, 128}):
+ *   b2r_bucket_partition : two passes over the ids partition the (row id, position) pairs into buckets of
+ *                          2^shift consecutive table rows (~200 pairs each) with L2 atomics;
+ *   b2r_bucket_apply     : one CTA per bucket sorts its pairs by (row, position) in shared memory and applies
+ *                          mode 1 (dense[row] += gradient row) or mode 2 (optimizer in place), each row's
+ *                          contributions summed in ascending position -> same bits on every run.
+ * The workspace must have been initialised once with b2r_bucket_workspace_init (zeroed counters); partition
+ * leaves the counters zero again, so the same workspace is reusable step after step.
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API size_t b2r_bucket_workspace_bytes(int64_t n, int64_t n_rows);
+B2R_API int b2r_bucket_workspace_init(void* ws, size_t ws_bytes, int64_t n, int64_t n_rows, b2r_stream_t stream);
+B2R_API int b2r_bucket_partition(const int64_t* ids, int64_t n, int64_t n_rows, int64_t ignore_id, int64_t ignore_n,
+                         void* ws, size_t ws_bytes, int32_t* err_flag, b2r_stream_t stream);
+B2R_API int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d, const b2r_grad_source* s0,
+                     const b2r_grad_source* s1, int mode, float* dense, float* W, float* m, float* v,
+                     const b2r_optim* opt, b2r_stream_t stream);
 
 /* Fast, order-nondeterministic alternative to plan+segment for mode 1 (dense += via red.global.add.v4.f32) */
 B2R_API int b2r_scatter_add_atomic(const int64_t* ids, int64_t n_rows, const b2r_grad_source* s, int d,

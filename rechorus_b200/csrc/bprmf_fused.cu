@@ -9,6 +9,8 @@
 // computes g for its own rows, accumulates g*row in registers, and the GPS partial dQ vectors are summed in
 // group order (deterministic).  replaces: BPRMF.py:39-42 forward, BaseModel.py:182-185 loss, and the
 // mul/sum + loss half of loss.backward() (BaseRunner.py:205).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2r {
@@ -22,8 +24,10 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
-template <int LPR, int RPG>
-__global__ void __launch_bounds__(256)
+// SPI samples per CTA pass are processed together: all their candidate rows are requested before the first
+// reduction (SPI*RPG independent 128-bit loads per lane) and every barrier is shared by SPI samples.
+template <int LPR, int RPG, int SPI>
+__global__ void __launch_bounds__(256, (RPG * SPI <= 8) ? 3 : 2)
 k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int64_t n_users,
               const float* __restrict__ T, const int64_t* __restrict__ ids, int64_t n_t,
               float* __restrict__ pred, float* __restrict__ gout, float* __restrict__ row_loss,
@@ -31,96 +35,108 @@ k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
     static_assert(RPG <= LPR, "ids of a group's rows are loaded one per lane");
     constexpr int D = LPR * 4;
     constexpr int GPC = 256 / LPR;
-    __shared__ float sp[GPC * RPG];          // scores of the samples this CTA holds (C <= GPS*RPG each)
-    __shared__ float4 part[GPC][LPR];        // partial dQ per group
+    __shared__ float sp[SPI][GPC * RPG];     // scores of the samples this CTA holds (C <= GPS*RPG each)
+    __shared__ float4 part[SPI][GPC][LPR];   // partial dQ per group
     const int sub = threadIdx.x % LPR;
     const int grp = threadIdx.x / LPR;
-    const int SPB = GPC / GPS;
+    const int SPB = GPC / GPS;               // sample slots per pass (x SPI samples each)
     const int j = grp % GPS;
     const int slot = grp / GPS;
-    float* myp = sp + slot * (GPS * RPG);
     const float invB = 1.f / (float)B;
-    for (int64_t sbase = (int64_t)blockIdx.x * SPB; sbase < B; sbase += (int64_t)gridDim.x * SPB) {
-        const int64_t b = sbase + slot;
-        const bool have = b < B;
-        const int c_mine = j + GPS * sub;                       // the candidate lane `sub` speaks for
-        const bool mine_ok = have && sub < RPG && c_mine < C;
-
-        int64_t qrow = 0;
-        if (have) qrow = checked_id(uid[b], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
-        const float4 q = ld4(U + qrow * D + sub * 4);
-        int64_t my_id = 0;
-        if (mine_ok) my_id = checked_id(ids[b * C + c_mine], n_t, err_flag);
-
-        float4 r[RPG];
+    const int c_mine = j + GPS * sub;        // the candidate lane `sub` speaks for
+    for (int64_t sbase = (int64_t)blockIdx.x * SPB * SPI; sbase < B; sbase += (int64_t)gridDim.x * SPB * SPI) {
+        int64_t bs[SPI];
+        bool have[SPI], mine_ok[SPI];
+        float4 q[SPI];
+        float4 r[SPI][RPG];
+        float mine[SPI];
 #pragma unroll
-        for (int k = 0; k < RPG; ++k) {
-            const int64_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
-            const bool ok = have && (j + GPS * k) < C;
-            r[k] = ok ? ld_row4(T + id_k * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float mine = 0.f;
+        for (int s = 0; s < SPI; ++s) {
+            bs[s] = sbase + (int64_t)s * SPB + slot;
+            have[s] = bs[s] < B;
+            mine_ok[s] = have[s] && sub < RPG && c_mine < C;
+            int64_t qrow = 0;
+            if (have[s]) qrow = checked_id(uid[bs[s]], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
+            q[s] = ld4(U + qrow * D + sub * 4);
+            int64_t my_id = 0;
+            if (mine_ok[s]) my_id = checked_id(ids[bs[s] * C + c_mine], n_t, err_flag);
 #pragma unroll
-        for (int k = 0; k < RPG; ++k) {
-            const float s = group_sum<LPR>(dot4(q, r[k]));
-            if (sub == k) mine = s;
+            for (int k = 0; k < RPG; ++k) {
+                const int64_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
+                const bool ok = have[s] && (j + GPS * k) < C;
+                r[s][k] = ok ? ld_row4(T + id_k * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        if (mine_ok) {
-            myp[c_mine] = mine;
-            if (pred != nullptr) pred[b * C + c_mine] = mine;
+#pragma unroll
+        for (int s = 0; s < SPI; ++s) {
+            mine[s] = 0.f;
+#pragma unroll
+            for (int k = 0; k < RPG; ++k) {
+                const float v = group_sum<LPR>(dot4(q[s], r[s][k]));
+                if (sub == k) mine[s] = v;
+            }
+            if (mine_ok[s]) {
+                sp[s][slot * (GPS * RPG) + c_mine] = mine[s];
+                if (pred != nullptr) pred[bs[s] * C + c_mine] = mine[s];
+            }
         }
         __syncthreads();
-
-        // loss statistics of this sample (every group of the sample computes them redundantly)
-        const float p = myp[0];
-        float mx = -INFINITY;
-        for (int c = 1 + sub; c < C; c += LPR) mx = fmaxf(mx, myp[c]);
-        mx = group_max<LPR>(mx);
-        float Z = 0.f, A = 0.f, Dp = 0.f;
-        for (int c = 1 + sub; c < C; c += LPR) {
-            const float n = myp[c];
-            const float e = expf(n - mx);
-            const float s = sigmoidf_f(p - n);
-            Z += e;
-            A = fmaf(e, s, A);
-            Dp = fmaf(e * s, 1.f - s, Dp);
-        }
-        Z = group_sum<LPR>(Z);
-        A = group_sum<LPR>(A);
-        Dp = group_sum<LPR>(Dp);
-        const float S = (C > 1) ? A / Z : 0.f;
-        const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
-        const float Sc = fminf(fmaxf(S, 1e-8f), 1.f - 1e-8f);
-        const float dS = inside ? -invB / S : 0.f;
-        const float invZ = (C > 1) ? 1.f / Z : 0.f;
-        float gmine = 0.f;
-        if (mine_ok) {
-            if (c_mine == 0) {
-                gmine = dS * Dp * invZ;
-            } else {
-                const float w = expf(mine - mx) * invZ;
-                const float s = sigmoidf_f(p - mine);
-                gmine = dS * w * ((s - S) - s * (1.f - s));
-            }
-            gout[b * C + c_mine] = gmine;
-        }
-        if (have && j == 0 && sub == 0) row_loss[b] = -logf(Sc);
-
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < RPG; ++k) {
-            const float gk = __shfl_sync(B2R_FULL_MASK, gmine, k, LPR);
-            fma4(acc, gk, r[k]);
-        }
-        part[grp][sub] = acc;
-        __syncthreads();
-        if (j == 0 && have) {
-            float4 tot = part[grp][sub];
-            for (int t = 1; t < GPS; ++t) {
-                const float4 x = part[grp + t][sub];
-                tot.x += x.x; tot.y += x.y; tot.z += x.z; tot.w += x.w;
+        for (int s = 0; s < SPI; ++s) {
+            // loss statistics of this sample (every group of the sample computes them redundantly)
+            const float* myp = sp[s] + slot * (GPS * RPG);
+            const float p = myp[0];
+            float mx = -INFINITY;
+            for (int c = 1 + sub; c < C; c += LPR) mx = fmaxf(mx, myp[c]);
+            mx = group_max<LPR>(mx);
+            float Z = 0.f, A = 0.f, Dp = 0.f;
+            for (int c = 1 + sub; c < C; c += LPR) {
+                const float n = myp[c];
+                const float e = expf(n - mx);
+                const float sg = sigmoidf_f(p - n);
+                Z += e;
+                A = fmaf(e, sg, A);
+                Dp = fmaf(e * sg, 1.f - sg, Dp);
             }
-            st4(dQ + b * D + sub * 4, tot);
+            Z = group_sum<LPR>(Z);
+            A = group_sum<LPR>(A);
+            Dp = group_sum<LPR>(Dp);
+            const float S = (C > 1) ? A / Z : 0.f;
+            const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
+            const float Sc = fminf(fmaxf(S, 1e-8f), 1.f - 1e-8f);
+            const float dS = inside ? -invB / S : 0.f;
+            const float invZ = (C > 1) ? 1.f / Z : 0.f;
+            float gmine = 0.f;
+            if (mine_ok[s]) {
+                if (c_mine == 0) {
+                    gmine = dS * Dp * invZ;
+                } else {
+                    const float w = expf(mine[s] - mx) * invZ;
+                    const float sg = sigmoidf_f(p - mine[s]);
+                    gmine = dS * w * ((sg - S) - sg * (1.f - sg));
+                }
+                gout[bs[s] * C + c_mine] = gmine;
+            }
+            if (have[s] && j == 0 && sub == 0) row_loss[bs[s]] = -logf(Sc);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < RPG; ++k) {
+                const float gk = __shfl_sync(B2R_FULL_MASK, gmine, k, LPR);
+                fma4(acc, gk, r[s][k]);
+            }
+            part[s][grp][sub] = acc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < SPI; ++s) {
+            if (j == 0 && have[s]) {
+                float4 tot = part[s][grp][sub];
+                for (int t = 1; t < GPS; ++t) {
+                    const float4 x = part[s][grp + t][sub];
+                    tot.x += x.x; tot.y += x.y; tot.z += x.z; tot.w += x.w;
+                }
+                st4(dQ + bs[s] * D + sub * 4, tot);
+            }
         }
         __syncthreads();
     }
@@ -167,22 +183,39 @@ extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64
     const int GPC = d == 32 ? 32 : (d == 64 ? 16 : (d == 128 ? 8 : 0));
     if (GPC == 0 || !pick_shape(C, GPC, d == 128 ? 16 : 8, &RPG, &GPS))
         return set_error(B2R_E_UNSUPPORTED, "b2r_bprmf_fused_fwd_bwd: no fused variant for d=%d C=%d", d, C);
+    static int spi_env = -1;                // tuning knob B2R_FUSED_SPI = 1 | 2 (read once)
+    if (spi_env < 0) {
+        const char* e = getenv("B2R_FUSED_SPI");
+        spi_env = e ? atoi(e) : 2;
+        if (spi_env != 1 && spi_env != 2) spi_env = 2;
+    }
+    const int SPI = (RPG <= 8) ? spi_env : 1;
     const int SPB = GPC / GPS;
-    const int64_t need = ((int64_t)B + SPB - 1) / SPB;
+    const int64_t need = ((int64_t)B + (int64_t)SPB * SPI - 1) / ((int64_t)SPB * SPI);
     const int64_t cap = (int64_t)sm_count() * 8;
     const int grid = (int)(need < cap ? need : cap);
 #define B2R_FUSED(LPR, R)                                                                              \
-    k_bprmf_fused<LPR, R><<<grid, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, \
-                                               GPS, err_flag)
+    do {                                                                                               \
+        if (SPI == 2)                                                                                  \
+            k_bprmf_fused<LPR, R, 2><<<grid, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, \
+                                                          dQ, B, C, GPS, err_flag);                    \
+        else                                                                                           \
+            k_bprmf_fused<LPR, R, 1><<<grid, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, \
+                                                          dQ, B, C, GPS, err_flag);                    \
+    } while (0)
+#define B2R_FUSED1(LPR, R)                                                                             \
+    k_bprmf_fused<LPR, R, 1><<<grid, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, \
+                                                  GPS, err_flag)
     if (d == 32) {
         if (RPG == 2) B2R_FUSED(8, 2); else if (RPG == 4) B2R_FUSED(8, 4); else B2R_FUSED(8, 8);
     } else if (d == 64) {
         if (RPG == 2) B2R_FUSED(16, 2); else if (RPG == 4) B2R_FUSED(16, 4); else B2R_FUSED(16, 8);
     } else {
         if (RPG == 2) B2R_FUSED(32, 2); else if (RPG == 4) B2R_FUSED(32, 4);
-        else if (RPG == 8) B2R_FUSED(32, 8); else B2R_FUSED(32, 16);
+        else if (RPG == 8) B2R_FUSED(32, 8); else B2R_FUSED1(32, 16);
     }
 #undef B2R_FUSED
+#undef B2R_FUSED1
     B2R_LAUNCH_OK("k_bprmf_fused");
     return 0;
 }

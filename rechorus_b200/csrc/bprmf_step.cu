@@ -5,7 +5,8 @@
 //   side :  plan(t+1) for the NEXT batch's ids (or plan(t) itself when nothing was prefetched)
 // The index plan (radix sort of the ids) only depends on the ids, so the context builds it one step ahead on
 // a library-owned non-blocking stream while the HBM-bound kernels of the current step run; joins are event
-// waits, never host synchronisations.  Plans are double-buffered in the caller-provided workspace.
+// waits, never host synchronisations.  Plans (bucket partitions, bucket.cu) are double-buffered in the caller-provided
+// workspace.  d must be 32, 64 or 128 (the widths the bucket kernels are built for).
 #include "common.cuh"
 
 extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64_t n_users, const float* I,
@@ -16,13 +17,13 @@ extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64
 namespace b2r {
 
 struct PlanBuf {
-    size_t ik, ip, is, inu, uk, up, us, unu;
+    size_t iws, uws;                 // bucket workspaces (b2r_bucket_partition) for the item / user table
 };
 
 struct StepLayout {
     size_t q, pred, g, rows, dQ;
     PlanBuf plan[2];
-    size_t iws, iws_bytes, uws, uws_bytes;
+    size_t iws_bytes, uws_bytes;
     size_t total;
 };
 
@@ -39,20 +40,12 @@ static bool step_layout(int B, int C, int d, int64_t n_users, int64_t n_items, S
     L->g = take(n * 4);
     L->rows = take((size_t)B * 4);
     L->dQ = take((size_t)B * d * 4);
+    L->iws_bytes = b2r_bucket_workspace_bytes((int64_t)n, n_items);
+    L->uws_bytes = b2r_bucket_workspace_bytes(B, n_users);
     for (int s = 0; s < 2; ++s) {
-        L->plan[s].ik = take(n * 4);
-        L->plan[s].ip = take(n * 4);
-        L->plan[s].is = take(n * 4);
-        L->plan[s].inu = take(4);
-        L->plan[s].uk = take((size_t)B * 4);
-        L->plan[s].up = take((size_t)B * 4);
-        L->plan[s].us = take((size_t)B * 4);
-        L->plan[s].unu = take(4);
+        L->plan[s].iws = take(L->iws_bytes);
+        L->plan[s].uws = take(L->uws_bytes);
     }
-    L->iws_bytes = b2r_plan_workspace_bytes((int64_t)n, n_items);
-    L->iws = take(L->iws_bytes);
-    L->uws_bytes = b2r_plan_workspace_bytes(B, n_users);
-    L->uws = take(L->uws_bytes);
     L->total = off;
     return L->iws_bytes != 0 && L->uws_bytes != 0;
 }
@@ -109,6 +102,19 @@ extern "C" int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t
         delete c;
         return set_error((int)e, "b2r_bprmf_ctx_create: %s", cudaGetErrorString(e));
     }
+    for (int sl = 0; sl < 2; ++sl) {      // bucket counters start at zero (the scan kernel re-zeroes them every step)
+        int rc = b2r_bucket_workspace_init(c->ws + c->L.plan[sl].iws, c->L.iws_bytes, (int64_t)B * C, n_items, c->side);
+        if (rc == 0) rc = b2r_bucket_workspace_init(c->ws + c->L.plan[sl].uws, c->L.uws_bytes, B, n_users, c->side);
+        if (rc != 0) {
+            delete c;
+            return rc;
+        }
+    }
+    e = cudaStreamSynchronize(c->side);
+    if (e != cudaSuccess) {
+        delete c;
+        return set_error((int)e, "b2r_bprmf_ctx_create: %s", cudaGetErrorString(e));
+    }
     *ctx_out = c;
     return 0;
 }
@@ -130,14 +136,10 @@ static int build_plans(StepCtx* c, int slot, const int64_t* uid, const int64_t* 
     const PlanBuf& p = c->L.plan[slot];
     const int64_t n = (int64_t)c->B * c->C;
     profile_begin(B2R_PROF_PLAN_I, c->side);
-    int rc = b2r_plan_build(iid, n, c->n_items, reinterpret_cast<uint32_t*>(base + p.ik),
-                            reinterpret_cast<uint32_t*>(base + p.ip), reinterpret_cast<int32_t*>(base + p.is),
-                            reinterpret_cast<int32_t*>(base + p.inu), base + c->L.iws, c->L.iws_bytes, err_flag, c->side);
+    int rc = b2r_bucket_partition(iid, n, c->n_items, -1, 0, base + p.iws, c->L.iws_bytes, err_flag, c->side);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_PLAN_I, c->side);
-    rc = b2r_plan_build(uid, c->B, c->n_users, reinterpret_cast<uint32_t*>(base + p.uk),
-                        reinterpret_cast<uint32_t*>(base + p.up), reinterpret_cast<int32_t*>(base + p.us),
-                        reinterpret_cast<int32_t*>(base + p.unu), base + c->L.uws, c->L.uws_bytes, err_flag, c->side);
+    rc = b2r_bucket_partition(uid, c->B, c->n_users, -1, 0, base + p.uws, c->L.uws_bytes, err_flag, c->side);
     if (rc != 0) return rc;
     B2R_CUDA_OK(cudaEventRecord(c->join[slot], c->side));
     return 0;
@@ -217,16 +219,12 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
     const PlanBuf& p = c->L.plan[cur];
     b2r_grad_source si{item_src, g, item_src_id, n, C, 0};
     profile_begin(B2R_PROF_SEGMENT_I, main_s);
-    rc = b2r_segment_apply(reinterpret_cast<uint32_t*>(base + p.ik), reinterpret_cast<uint32_t*>(base + p.ip),
-                           reinterpret_cast<int32_t*>(base + p.is), reinterpret_cast<int32_t*>(base + p.inu), n,
-                           t->n_items, d, &si, nullptr, 2, nullptr, nullptr, nullptr, t->I, t->Im, t->Iv, opt, main_s);
+    rc = b2r_bucket_apply(base + p.iws, n, t->n_items, d, &si, nullptr, 2, nullptr, t->I, t->Im, t->Iv, opt, main_s);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_SEGMENT_I, main_s);
     b2r_grad_source su{dQ, nullptr, nullptr, B, 1, 0};
     profile_begin(B2R_PROF_SEGMENT_U, main_s);
-    rc = b2r_segment_apply(reinterpret_cast<uint32_t*>(base + p.uk), reinterpret_cast<uint32_t*>(base + p.up),
-                           reinterpret_cast<int32_t*>(base + p.us), reinterpret_cast<int32_t*>(base + p.unu), B,
-                           t->n_users, d, &su, nullptr, 2, nullptr, nullptr, nullptr, t->U, t->Um, t->Uv, opt, main_s);
+    rc = b2r_bucket_apply(base + p.uws, B, t->n_users, d, &su, nullptr, 2, nullptr, t->U, t->Um, t->Uv, opt, main_s);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_SEGMENT_U, main_s);
     return 0;

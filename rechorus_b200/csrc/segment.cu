@@ -77,8 +77,8 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
         float4 w, m, v;
         if (MODE == 2) {
             w = ld4(W + row * D + sub * 4);
-            if (opt.kind == 1) m = ld4(M + row * D + sub * 4);
-            if (opt.kind != 0) v = ld4(V + row * D + sub * 4);
+            if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+            if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
         } else if (MODE == 1) {
             w = ld4(dense + row * D + sub * 4);
         }
@@ -99,8 +99,8 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
         } else {
             optim_update(opt, w, m, v, acc);
             st4(W + row * D + sub * 4, w);
-            if (opt.kind == 1) st4(M + row * D + sub * 4, m);
-            if (opt.kind != 0) st4(V + row * D + sub * 4, v);
+            if (opt.kind == 1) st4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4, m);
+            if (opt.kind != 0) st4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4, v);
         }
     }
 }
@@ -145,8 +145,8 @@ k_segment_optim(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
             acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row[k] < n_rows) {
                 w[k] = ld4(W + row[k] * D + sub * 4);
-                if (opt.kind == 1) m[k] = ld4(M + row[k] * D + sub * 4);
-                if (opt.kind != 0) v[k] = ld4(V + row[k] * D + sub * 4);
+                if (opt.kind == 1) m[k] = ld4(M + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+                if (opt.kind != 0) v[k] = ld4(V + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4);
             }
         }
         // contributions, t-th of every row in parallel (ascending position within a row -> deterministic)
@@ -177,8 +177,8 @@ k_segment_optim(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
             if (row[k] < n_rows) {
                 optim_update(opt, w[k], m[k], v[k], acc[k]);
                 st4(W + row[k] * D + sub * 4, w[k]);
-                if (opt.kind == 1) st4(M + row[k] * D + sub * 4, m[k]);
-                if (opt.kind != 0) st4(V + row[k] * D + sub * 4, v[k]);
+                if (opt.kind == 1) st4(M + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4, m[k]);
+                if (opt.kind != 0) st4(V + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4, v[k]);
             }
         }
     }
@@ -218,12 +218,12 @@ k_segment_apply_generic(const uint32_t* __restrict__ sorted_key, const uint32_t*
                 st4(dense + row * d + k * 4, w);
             } else {
                 float4 w = ld4(W + row * d + k * 4), m, v;
-                if (opt.kind == 1) m = ld4(M + row * d + k * 4);
-                if (opt.kind != 0) v = ld4(V + row * d + k * 4);
+                if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : d) + k * 4);
+                if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : d) + k * 4);
                 optim_update(opt, w, m, v, acc);
                 st4(W + row * d + k * 4, w);
-                if (opt.kind == 1) st4(M + row * d + k * 4, m);
-                if (opt.kind != 0) st4(V + row * d + k * 4, v);
+                if (opt.kind == 1) st4(M + row * (opt.state_ld ? opt.state_ld : d) + k * 4, m);
+                if (opt.kind != 0) st4(V + row * (opt.state_ld ? opt.state_ld : d) + k * 4, v);
             }
         }
     }
@@ -401,6 +401,7 @@ extern "C" int b2r_dense_optim(float* W, const float* grad, float* m, float* v, 
     B2R_REQUIRE(opt->kind >= 0 && opt->kind <= 2, B2R_E_BADARG, "b2r_dense_optim: optimizer kind %d", opt->kind);
     B2R_REQUIRE(opt->kind != 1 || (m && v), B2R_E_BADARG, "b2r_dense_optim: Adam needs m and v");
     B2R_REQUIRE(opt->kind != 2 || v, B2R_E_BADARG, "b2r_dense_optim: Adagrad needs v");
+    B2R_REQUIRE(opt->state_ld == 0, B2R_E_BADARG, "b2r_dense_optim: interleaved optimizer state is row-sparse only");
     B2R_REQUIRE(aligned16(W) && aligned16(grad), B2R_E_BADARG, "b2r_dense_optim: 16-byte alignment");
     if (numel <= 0) return 0;
     int64_t need = ((numel >> 2) + 255) / 256;

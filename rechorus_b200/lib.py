@@ -24,7 +24,8 @@ class GradSource(C.Structure):
 class Optim(C.Structure):
     """b2r_optim (include/b200rec.h)"""
     _fields_ = [("kind", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
-                ("eps", C.c_float), ("weight_decay", C.c_float), ("bc1", C.c_float), ("bc2", C.c_float)]
+                ("eps", C.c_float), ("weight_decay", C.c_float), ("bc1", C.c_float), ("bc2", C.c_float),
+                ("state_ld", C.c_int32)]
 
 
 class BprmfTables(C.Structure):
@@ -62,6 +63,13 @@ SIGNATURES = {
                                     C.POINTER(GradSource), C.POINTER(GradSource), C.c_int, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(Optim), C.c_void_p]),
+    "b2r_bucket_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "b2r_bucket_workspace_init": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int64, C.c_int64, C.c_void_p]),
+    "b2r_bucket_partition": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                       C.c_size_t, C.c_void_p, C.c_void_p]),
+    "b2r_bucket_apply": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.POINTER(GradSource),
+                                   C.POINTER(GradSource), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(Optim), C.c_void_p]),
     "b2r_scatter_add_atomic": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(GradSource), C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "b2r_dense_optim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

@@ -222,6 +222,63 @@ class IndexPlan:
         self._apply(W.shape[1], sources, 2, W=W, m=m, v=v, opt=opt)
 
 
+_bucket_ws = {}
+
+
+class BucketPlan:
+    """Bucketed partition of a batch's (row id, position) pairs (b2r_bucket_partition) -- the hot-path sibling of
+    IndexPlan for the dense-add and fused-optimizer outputs (d in {32, 64, 128}).  The workspace is cached per
+    (device, stream, n, n_rows) and reused in stream order."""
+
+    SUPPORTED_D = (32, 64, 128)
+
+    def __init__(self, ids: torch.Tensor, n_rows: int, ignore_id: int = -1, ignore_n: int = 0):
+        _need_cuda(ids)
+        ids = _i64c(ids.reshape(-1), "ids")
+        n = ids.numel()
+        if n == 0:
+            raise ValueError("empty id list")
+        self.n, self.n_rows, self.device = n, int(n_rows), ids.device
+        L = _lib.load()
+        key = (ids.device.index, _stream(), n, self.n_rows)
+        ws = _bucket_ws.get(key)
+        if ws is None:
+            nbytes = L.b2r_bucket_workspace_bytes(n, self.n_rows)
+            if nbytes == 0:
+                raise _lib.B200RecError(f"b2r_bucket_workspace_bytes({n}, {n_rows}) = 0")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
+            _lib.check(L.b2r_bucket_workspace_init(_p(ws), nbytes, n, self.n_rows, _stream()),
+                       "b2r_bucket_workspace_init")
+            _bucket_ws[key] = ws
+        self.ws = ws
+        self._ids = ids
+        _lib.check(L.b2r_bucket_partition(_p(ids), n, self.n_rows, int(ignore_id), int(ignore_n), _p(ws), ws.numel(),
+                                          _p(err_flag(ids.device)), _stream()), "b2r_bucket_partition")
+
+    def _apply(self, d, sources, mode, dense=None, W=None, m=None, v=None, opt=None):
+        if not 1 <= len(sources) <= 2:
+            raise ValueError("one or two sources")
+        s0 = sources[0].c_struct()
+        s1 = sources[1].c_struct() if len(sources) == 2 else None
+        L = _lib.load()
+        _lib.check(L.b2r_bucket_apply(_p(self.ws), self.n, self.n_rows, d, C.byref(s0),
+                                      C.byref(s1) if s1 is not None else None, mode, _p(dense), _p(W), _p(m), _p(v),
+                                      C.byref(opt) if opt is not None else None, _stream()), "b2r_bucket_apply")
+
+    def add_to_dense(self, dense: torch.Tensor, sources: Sequence[Source]) -> None:
+        self._apply(dense.shape[1], sources, 1, dense=dense)
+
+    def apply_optimizer(self, W: torch.Tensor, m, v, opt: _lib.Optim, sources: Sequence[Source]) -> None:
+        self._apply(W.shape[1], sources, 2, W=W, m=m, v=v, opt=opt)
+
+
+def make_plan(ids: torch.Tensor, n_rows: int, d: int, ignore_id: int = -1, ignore_n: int = 0):
+    """BucketPlan where the bucket kernels exist (d = 32/64/128), IndexPlan (device radix sort) otherwise"""
+    if d in BucketPlan.SUPPORTED_D:
+        return BucketPlan(ids, n_rows, ignore_id, ignore_n)
+    return IndexPlan(ids, n_rows, ignore_id, ignore_n)
+
+
 def scatter_add_atomic(dense: torch.Tensor, ids: torch.Tensor, source: Source) -> None:
     """order-nondeterministic dense += via red.global.add.v4.f32 (b2r_scatter_add_atomic)"""
     ids = _i64c(ids.reshape(-1), "ids")
@@ -263,12 +320,13 @@ def _table_grad(table: torch.Tensor, ids: torch.Tensor, source: Source, ignore_i
     if mode == "fused":
         table._b2r_pending.append((ids.reshape(-1), source, ignore_id))
         return None
-    plan = IndexPlan(ids, table.shape[0], ignore_id, ids.numel() if ignore_id >= 0 else 0)
+    ign_n = ids.numel() if ignore_id >= 0 else 0
     if mode == "sparse":
+        plan = IndexPlan(ids, table.shape[0], ignore_id, ign_n)
         uniq, rows = plan.reduce_rows(table.shape[1], [source])
         return torch.sparse_coo_tensor(uniq.unsqueeze(0), rows, size=tuple(table.shape), is_coalesced=True)
     dense = torch.zeros_like(table)
-    plan.add_to_dense(dense, [source])
+    make_plan(ids, table.shape[0], table.shape[1], ignore_id, ign_n).add_to_dense(dense, [source])
     return dense
 
 
@@ -404,8 +462,8 @@ def bprmf_train_step(U: torch.nn.Parameter, I: torch.nn.Parameter, optimizer, ui
     B, Cn = iid.shape
     d = U.shape[1]
     eu, ei = optimizer.entry(U), optimizer.entry(I)
-    if eu["wd"] != ei["wd"]:
-        raise _lib.B200RecError("fused step expects one weight decay for both tables")
+    if eu["wd"] != ei["wd"] or eu["state_ld"] != ei["state_ld"]:
+        raise _lib.B200RecError("fused step expects one weight decay / state layout for both tables")
     L = _lib.load()
     key = (U.device.index, B, Cn, d, U.shape[0], I.shape[0], _stream())
     ctx = _step_ctx.get(key)
@@ -418,7 +476,7 @@ def bprmf_train_step(U: torch.nn.Parameter, I: torch.nn.Parameter, optimizer, ui
     else:
         next_uid = next_iid = None
     optimizer.advance()
-    opt = optimizer._opt(ei["wd"])
+    opt = optimizer._opt(ei["wd"], ei["state_ld"])
     tables = _lib.BprmfTables(_p(U.data), _p(I.data), _p(eu["m"]), _p(eu["v"]), _p(ei["m"]), _p(ei["v"]),
                               U.shape[0], I.shape[0], d, 0)
     loss = torch.empty((), dtype=torch.float32, device=U.device)
@@ -516,6 +574,7 @@ class _AddLayerNorm(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, res, gamma, beta, eps):
+        _need_cuda(x, res, gamma, beta)
         d = x.shape[-1]
         x2, r2 = _f32c(x.reshape(-1, d), "x"), _f32c(res.reshape(-1, d), "res")
         rows = x2.shape[0]
@@ -555,6 +614,7 @@ class _CausalAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, H):
+        _need_cuda(q, k, v)
         B, Ln, d = q.shape
         q, k, v = _f32c(q, "q"), _f32c(k, "k"), _f32c(v, "v")
         out = torch.empty((B, Ln, d), dtype=torch.float32, device=q.device)
@@ -586,6 +646,7 @@ class _EmbedHistory(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, I, P, hist, lengths):
+        _need_cuda(I, P, hist, lengths)
         hist, lengths = _i64c(hist, "history_items"), _i64c(lengths, "lengths")
         B, Ln = hist.shape
         d = I.shape[1]
@@ -626,6 +687,7 @@ class _SelectLast(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, hist, lengths):
+        _need_cuda(y, hist, lengths)
         y = _f32c(y, "y")
         B, Ln, d = y.shape
         h = torch.empty((B, d), dtype=torch.float32, device=y.device)
@@ -655,6 +717,7 @@ class _ColScale(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, w):
+        _need_cuda(a, w)
         a, w = _f32c(a, "a"), _f32c(w, "w")
         out = torch.empty_like(a)
         L = _lib.load()
@@ -688,6 +751,7 @@ class _GatherConcat(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, Tu, Ti, uid, iid):
+        _need_cuda(Tu, Ti, uid, iid)
         uid, iid = _i64c(uid, "user_id"), _i64c(iid, "item_id")
         B, Cn = iid.shape
         d = Tu.shape[1]

@@ -41,11 +41,17 @@ class RowSparseOptimizer:
             if not p.requires_grad:
                 continue
             wd = 0.0 if "bias" in pname else self.l2
-            e = {"name": pname, "p": p, "wd": wd, "m": None, "v": None}
-            if self.kind == _lib.OPT_ADAM:
-                e["m"] = torch.zeros_like(p.data)
-            if self.kind != _lib.OPT_SGD:
-                e["v"] = torch.zeros_like(p.data)
+            e = {"name": pname, "p": p, "wd": wd, "m": None, "v": None, "state_ld": 0}
+            if self.kind == _lib.OPT_ADAM and ops.table_mode(p) == "fused" and p.dim() == 2:
+                # row-sparse Adam touches m[row] and v[row] together: keep them interleaved per row
+                # ([n_rows][2][d]) so each row's state is one contiguous 2*4d-byte burst in HBM
+                mv = torch.zeros((p.shape[0], 2, p.shape[1]), dtype=p.dtype, device=p.device)
+                e["mv"], e["m"], e["v"], e["state_ld"] = mv, mv[:, 0, :], mv[:, 1, :], 2 * p.shape[1]
+            else:
+                if self.kind == _lib.OPT_ADAM:
+                    e["m"] = torch.zeros_like(p.data)
+                if self.kind != _lib.OPT_SGD:
+                    e["v"] = torch.zeros_like(p.data)
             self._entries.append(e)
 
     # -- torch.optim-like surface used by BaseRunner.fit ------------------------------------------------
@@ -57,9 +63,9 @@ class RowSparseOptimizer:
             if pend:
                 pend.clear()
 
-    def _opt(self, wd: float) -> _lib.Optim:
+    def _opt(self, wd: float, state_ld: int = 0) -> _lib.Optim:
         b1, b2 = self.betas
-        return _lib.Optim(self.kind, self.lr, b1, b2, self.eps, wd, 1.0 - b1 ** self.t, 1.0 - b2 ** self.t)
+        return _lib.Optim(self.kind, self.lr, b1, b2, self.eps, wd, 1.0 - b1 ** self.t, 1.0 - b2 ** self.t, state_ld)
 
     @torch.no_grad()
     def step(self) -> None:
@@ -78,14 +84,16 @@ class RowSparseOptimizer:
                     raise _lib.B200RecError(f"{e['name']}: two padded gradient streams into one table")
                 ids = pend[0][0] if len(pend) == 1 else torch.cat([pend[0][0], pend[1][0]])
                 ign = pend[0][2]
-                plan = ops.IndexPlan(ids, p.shape[0], ign, pend[0][0].numel() if ign >= 0 else 0)
-                plan.apply_optimizer(p.data, e["m"], e["v"], self._opt(e["wd"]), [x[1] for x in pend])
+                plan = ops.make_plan(ids, p.shape[0], p.shape[1], ign, pend[0][0].numel() if ign >= 0 else 0)
+                plan.apply_optimizer(p.data, e["m"], e["v"], self._opt(e["wd"], e["state_ld"]), [x[1] for x in pend])
                 pend.clear()
             elif p.grad is not None:
                 if p.grad.is_sparse:
                     raise _lib.B200RecError(f"{e['name']}: sparse .grad -- use table mode 'fused' or 'dense' "
                                             "with RowSparseOptimizer, or torch.optim.SparseAdam")
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if e["state_ld"]:
+                    raise _lib.B200RecError(f"{e['name']}: table left 'fused' mode after the optimizer was built")
                 ops.dense_optim(p.data, g, e["m"], e["v"], self._opt(e["wd"]))
 
     def entry(self, param: torch.Tensor) -> dict:

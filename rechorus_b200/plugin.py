@@ -36,7 +36,7 @@ class _KernelModelMixin:
     """Shared by every kernel-backed model: table registry + loss + optional inference hook."""
 
     def _register_tables(self, *params: nn.Parameter, mode: str = "dense") -> None:
-        self._b2r_tables: List[nn.Parameter] = list(params)
+        self.__dict__["_b2r_tables"] = list(params)
         for p in params:
             ops.set_table_mode(p, mode)
 
@@ -48,6 +48,27 @@ class _KernelModelMixin:
         'fused' (row-sparse fused optimizer, rechorus_b200.optim.RowSparseOptimizer)."""
         for p in self.sparse_tables():
             ops.set_table_mode(p, mode)
+
+    # ``model.optimizer`` is the seam helpers/BaseRunner.py:176-177 checks: when the tables are in 'fused' mode
+    # the (reference's or our) runner must find a RowSparseOptimizer there instead of building torch.optim,
+    # which would silently skip parameters whose .grad stays None.  Built lazily, after main.py:68 moved the
+    # model to the device.
+    @property
+    def optimizer(self):
+        opt = self.__dict__.get("_b2r_optimizer")
+        if opt is None and any(ops.table_mode(p) == "fused" for p in self.sparse_tables()):
+            tables = self.sparse_tables()
+            if tables and tables[0].is_cuda:
+                from .optim import RowSparseOptimizer
+                a = self.__dict__.get("_b2r_args")
+                opt = RowSparseOptimizer(self, getattr(a, "optimizer", "Adam"), lr=getattr(a, "lr", 1e-3),
+                                         l2=getattr(a, "l2", 0.0))
+                self.__dict__["_b2r_optimizer"] = opt
+        return opt
+
+    @optimizer.setter
+    def optimizer(self, value):
+        self.__dict__["_b2r_optimizer"] = value
 
     # models/BaseModel.py:175-189
     def loss(self, out_dict: dict) -> torch.Tensor:
@@ -70,6 +91,7 @@ class BPRMFKernels(_KernelModelMixin):
         return parser
 
     def _base_init(self, args, corpus):
+        self.__dict__["_b2r_args"] = args
         self.emb_size = args.emb_size
         if self.emb_size % 4 != 0:
             raise ValueError("rechorus_b200 kernels need emb_size % 4 == 0")
@@ -118,6 +140,7 @@ class NeuMFKernels(_KernelModelMixin):
 
     def _neumf_init(self, args, corpus):
         import ast
+        self.__dict__["_b2r_args"] = args
         self.emb_size = args.emb_size
         if self.emb_size % 4 != 0:
             raise ValueError("rechorus_b200 kernels need emb_size % 4 == 0")
@@ -198,6 +221,7 @@ class SASRecKernels(_KernelModelMixin):
         return parser
 
     def _base_init(self, args, corpus):
+        self.__dict__["_b2r_args"] = args
         self.emb_size = args.emb_size
         self.max_his = args.history_max
         self.num_layers = args.num_layers

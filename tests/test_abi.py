@@ -35,7 +35,7 @@ def test_binding_table_matches_header(built_lib):
     assert sorted(L.SIGNATURES) == _declared()
     handle = L.load()
     assert handle.b2r_version() == 100
-    assert ctypes.sizeof(L.GradSource) == 40 and ctypes.sizeof(L.Optim) == 32
+    assert ctypes.sizeof(L.GradSource) == 40 and ctypes.sizeof(L.Optim) == 36
 
 
 def test_bad_arguments_are_rejected_without_a_gpu(built_lib):
