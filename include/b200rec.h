@@ -82,6 +82,12 @@ B2R_API int b2r_gather_rows(const float* T, const int64_t* ids, int64_t n_t, flo
 B2R_API int b2r_gather_rows_strided(const float* T, const int64_t* ids, int64_t n_t, float* out, int out_ld,
                             int64_t n, int d, int ids_div, int32_t* err_flag, b2r_stream_t stream);
 
+/* Flat pair scoring out[e] = < Q[qidx[e]], T[rows[e]] >, rows[e] < 0 = unused slot (score 0).  The shard owner's
+ * half of BPRMF.py:39-42 when the item table is row-range sharded across GPUs (BASELINE config 5): the pairs are
+ * what the all-to-all delivered, Q is the all-gathered user-vector block. */
+B2R_API int b2r_pairdot_fwd(const float* Q, const int64_t* qidx, int64_t n_q, const float* T, const int64_t* rows,
+                    int64_t n_t, float* out, int64_t n, int d, int32_t* err_flag, b2r_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * BPR loss + closed-form gradient (models/BaseModel.py:175-189; formula SURVEY.md A.4).
  * pred [B,C] (column 0 = positive).  loss_out: 1 float.  grad_pred [B,C] = d loss / d pred (may be NULL).

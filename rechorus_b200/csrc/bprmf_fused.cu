@@ -24,8 +24,11 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
-// SPI samples per CTA pass are processed together: all their candidate rows are requested before the first
-// reduction (SPI*RPG independent 128-bit loads per lane) and every barrier is shared by SPI samples.
+// SPI samples per lane-group slot are processed together per CTA pass: all their candidate rows are requested
+// before the first reduction (SPI*RPG independent 128-bit loads per lane) and every barrier is shared.
+// Phases per pass:  rows -> scores (shared memory)  |barrier|  one WARP per sample: softmax/sigmoid statistics and
+// the gradient g of every candidate, each transcendental evaluated once  |barrier|  lane groups: acc = sum g*row
+// |barrier|  ordered combine of the GPS partials -> dQ.
 template <int LPR, int RPG, int SPI>
 __global__ void __launch_bounds__(256, (RPG * SPI <= 8) ? 3 : 2)
 k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int64_t n_users,
@@ -35,31 +38,32 @@ k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
     static_assert(RPG <= LPR, "ids of a group's rows are loaded one per lane");
     constexpr int D = LPR * 4;
     constexpr int GPC = 256 / LPR;
-    __shared__ float sp[SPI][GPC * RPG];     // scores of the samples this CTA holds (C <= GPS*RPG each)
-    __shared__ float4 part[SPI][GPC][LPR];   // partial dQ per group
+    constexpr int CPL = (GPC * RPG + 31) / 32;          // candidates per lane in the statistics warp (C <= GPC*RPG)
+    __shared__ float sp[SPI][GPC * RPG];                // scores, then gradients, of the samples this CTA holds
+    __shared__ float4 part[SPI][GPC][LPR];              // partial dQ per group
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = threadIdx.x % LPR;
     const int grp = threadIdx.x / LPR;
-    const int SPB = GPC / GPS;               // sample slots per pass (x SPI samples each)
+    const int SPB = GPC / GPS;                          // sample slots per pass (x SPI samples each)
     const int j = grp % GPS;
     const int slot = grp / GPS;
     const float invB = 1.f / (float)B;
-    const int c_mine = j + GPS * sub;        // the candidate lane `sub` speaks for
+    const int c_mine = j + GPS * sub;                   // the candidate lane `sub` speaks for
     for (int64_t sbase = (int64_t)blockIdx.x * SPB * SPI; sbase < B; sbase += (int64_t)gridDim.x * SPB * SPI) {
         int64_t bs[SPI];
-        bool have[SPI], mine_ok[SPI];
+        bool have[SPI];
         float4 q[SPI];
         float4 r[SPI][RPG];
-        float mine[SPI];
 #pragma unroll
         for (int s = 0; s < SPI; ++s) {
             bs[s] = sbase + (int64_t)s * SPB + slot;
             have[s] = bs[s] < B;
-            mine_ok[s] = have[s] && sub < RPG && c_mine < C;
+            const bool mine_ok = have[s] && sub < RPG && c_mine < C;
             int64_t qrow = 0;
             if (have[s]) qrow = checked_id(uid[bs[s]], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
             q[s] = ld4(U + qrow * D + sub * 4);
             int64_t my_id = 0;
-            if (mine_ok[s]) my_id = checked_id(ids[bs[s] * C + c_mine], n_t, err_flag);
+            if (mine_ok) my_id = checked_id(ids[bs[s] * C + c_mine], n_t, err_flag);
 #pragma unroll
             for (int k = 0; k < RPG; ++k) {
                 const int64_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
@@ -69,59 +73,82 @@ k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
         }
 #pragma unroll
         for (int s = 0; s < SPI; ++s) {
-            mine[s] = 0.f;
+            float mine = 0.f;
 #pragma unroll
             for (int k = 0; k < RPG; ++k) {
                 const float v = group_sum<LPR>(dot4(q[s], r[s][k]));
-                if (sub == k) mine[s] = v;
+                if (sub == k) mine = v;
             }
-            if (mine_ok[s]) {
-                sp[s][slot * (GPS * RPG) + c_mine] = mine[s];
-                if (pred != nullptr) pred[bs[s] * C + c_mine] = mine[s];
+            if (have[s] && sub < RPG && c_mine < C) {
+                sp[s][slot * (GPS * RPG) + c_mine] = mine;
+                if (pred != nullptr) pred[bs[s] * C + c_mine] = mine;
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int s = 0; s < SPI; ++s) {
-            // loss statistics of this sample (every group of the sample computes them redundantly)
-            const float* myp = sp[s] + slot * (GPS * RPG);
+        // ---- statistics + gradient: warp w owns sample slots w, w+8, ... of this pass ----------------------
+        for (int ss = warp; ss < SPB * SPI; ss += 8) {
+            const int s = ss / SPB, sl = ss % SPB;
+            const int64_t b = sbase + (int64_t)s * SPB + sl;
+            if (b >= B) continue;                           // warp-uniform
+            float* myp = sp[s] + sl * (GPS * RPG);
             const float p = myp[0];
+            float x[CPL], e[CPL], sg[CPL];
             float mx = -INFINITY;
-            for (int c = 1 + sub; c < C; c += LPR) mx = fmaxf(mx, myp[c]);
-            mx = group_max<LPR>(mx);
-            float Z = 0.f, A = 0.f, Dp = 0.f;
-            for (int c = 1 + sub; c < C; c += LPR) {
-                const float n = myp[c];
-                const float e = expf(n - mx);
-                const float sg = sigmoidf_f(p - n);
-                Z += e;
-                A = fmaf(e, sg, A);
-                Dp = fmaf(e * sg, 1.f - sg, Dp);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = 1 + lane + 32 * i;
+                x[i] = (c < C) ? myp[c] : -INFINITY;
+                mx = fmaxf(mx, x[i]);
             }
-            Z = group_sum<LPR>(Z);
-            A = group_sum<LPR>(A);
-            Dp = group_sum<LPR>(Dp);
+            mx = warp_max(mx);
+            float Z = 0.f, A = 0.f, Dp = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = 1 + lane + 32 * i;
+                e[i] = 0.f;
+                sg[i] = 0.f;
+                if (c < C) {
+                    e[i] = expf(x[i] - mx);
+                    sg[i] = sigmoidf_f(p - x[i]);
+                    Z += e[i];
+                    A = fmaf(e[i], sg[i], A);
+                    Dp = fmaf(e[i] * sg[i], 1.f - sg[i], Dp);
+                }
+            }
+            Z = warp_sum(Z);
+            A = warp_sum(A);
+            Dp = warp_sum(Dp);
             const float S = (C > 1) ? A / Z : 0.f;
             const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
             const float Sc = fminf(fmaxf(S, 1e-8f), 1.f - 1e-8f);
             const float dS = inside ? -invB / S : 0.f;
             const float invZ = (C > 1) ? 1.f / Z : 0.f;
-            float gmine = 0.f;
-            if (mine_ok[s]) {
-                if (c_mine == 0) {
-                    gmine = dS * Dp * invZ;
-                } else {
-                    const float w = expf(mine[s] - mx) * invZ;
-                    const float sg = sigmoidf_f(p - mine[s]);
-                    gmine = dS * w * ((sg - S) - sg * (1.f - sg));
+            __syncwarp();                                   // all lanes have read their scores: overwrite with g
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const int c = 1 + lane + 32 * i;
+                if (c < C) {
+                    const float g = dS * (e[i] * invZ) * ((sg[i] - S) - sg[i] * (1.f - sg[i]));
+                    myp[c] = g;
+                    gout[b * C + c] = g;
                 }
-                gout[bs[s] * C + c_mine] = gmine;
             }
-            if (have[s] && j == 0 && sub == 0) row_loss[bs[s]] = -logf(Sc);
+            if (lane == 0) {
+                const float g0 = dS * Dp * invZ;
+                myp[0] = g0;
+                gout[b * C] = g0;
+                row_loss[b] = -logf(Sc);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < SPI; ++s) {
+            const float* myg = sp[s] + slot * (GPS * RPG);
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < RPG; ++k) {
-                const float gk = __shfl_sync(B2R_FULL_MASK, gmine, k, LPR);
+                const int c = j + GPS * k;
+                const float gk = (have[s] && c < C) ? myg[c] : 0.f;
                 fma4(acc, gk, r[s][k]);
             }
             part[s][grp][sub] = acc;
@@ -132,8 +159,8 @@ k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
             if (j == 0 && have[s]) {
                 float4 tot = part[s][grp][sub];
                 for (int t = 1; t < GPS; ++t) {
-                    const float4 x = part[s][grp + t][sub];
-                    tot.x += x.x; tot.y += x.y; tot.z += x.z; tot.w += x.w;
+                    const float4 y = part[s][grp + t][sub];
+                    tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
                 }
                 st4(dQ + bs[s] * D + sub * 4, tot);
             }

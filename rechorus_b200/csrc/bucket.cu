@@ -26,6 +26,8 @@ struct BSrc {
 constexpr int kCap = 2048;        // pairs a CTA sorts in shared memory (16 KB)
 constexpr int kLong = 48;         // rows with at least this many contributions are reduced by the whole CTA
 constexpr int kBT = 256;
+constexpr int kPad = 32;          // ints per bucket counter: one 128-byte line each (L2 atomics serialise per line)
+constexpr int kRB = 4;            // unique rows a lane group keeps in flight in k_bucket_apply
 
 __device__ __forceinline__ void b_contribution(const BSrc& s0, const BSrc& s1, uint32_t p, const float*& base,
                                                int& ld, int64_t& row, float& c) {
@@ -74,7 +76,7 @@ k_bucket_count(const int64_t* __restrict__ ids, int64_t n, int64_t n_rows, int s
         const int64_t id = ids[i];
         if (i < ignore_n && id == ignore_id) continue;
         const int64_t key = checked_id(id, n_rows, err_flag);
-        atomicAdd(&count[key >> shift], 1);
+        atomicAdd(&count[(key >> shift) * kPad], 1);
     }
 }
 
@@ -88,7 +90,7 @@ k_bucket_scan(int* __restrict__ count, int* __restrict__ cursor, int* __restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < nb; base += 1024) {
         const int i = base + threadIdx.x;
-        const int v = i < nb ? count[i] : 0;
+        const int v = i < nb ? count[(int64_t)i * kPad] : 0;
         int x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -110,8 +112,8 @@ k_bucket_scan(int* __restrict__ count, int* __restrict__ cursor, int* __restrict
         const int excl = carry + (warp > 0 ? wsum[warp - 1] : 0) + x - v;
         if (i < nb) {
             off[i] = excl;
-            cursor[i] = excl;
-            count[i] = 0;
+            cursor[(int64_t)i * kPad] = excl;
+            count[(int64_t)i * kPad] = 0;
         }
         __syncthreads();
         if (threadIdx.x == 1023) carry += wsum[31];
@@ -127,7 +129,7 @@ k_bucket_scatter(const int64_t* __restrict__ ids, int64_t n, int64_t n_rows, int
         const int64_t id = ids[i];
         if (i < ignore_n && id == ignore_id) continue;
         const int64_t key = (id < 0 || id >= n_rows) ? 0 : id;
-        const int slot = atomicAdd(&cursor[key >> shift], 1);
+        const int slot = atomicAdd(&cursor[(key >> shift) * kPad], 1);
         pairs[slot] = ((uint64_t)key << 32) | (uint64_t)(uint32_t)i;
     }
 }
@@ -173,7 +175,7 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, int P) {
 }
 
 template <int LPR, int MODE>
-__global__ void __launch_bounds__(kBT, 3)
+__global__ void __launch_bounds__(kBT, 2)
 k_bucket_apply(const uint64_t* __restrict__ pairs, const int* __restrict__ off, int nb, BSrc s0, BSrc s1,
                float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense,
                b2r_optim opt) {
@@ -227,36 +229,58 @@ k_bucket_apply(const uint64_t* __restrict__ pairs, const int* __restrict__ off, 
             if (tid == kBT - 1) sh_nu = wbase + x;
             __syncthreads();
             const int nu = sh_nu;
-            // ---- short rows: one lane group per unique row ------------------------------------
-            for (int u = grp; u < nu; u += GPC) {
-                const int j0 = heads[u];
-                const int j1 = (u + 1 < nu) ? heads[u + 1] : cnt;
-                if (j1 - j0 >= kLong) {
-                    if (sub == 0) {
-                        const int q = atomicAdd(&sh_nlong, 1);
-                        if (q < 64) longs[q] = (unsigned short)u;
+            // ---- short rows: kRB consecutive unique rows per lane group, all their loads in flight together ----
+            for (int u0 = grp * kRB; u0 < nu; u0 += GPC * kRB) {
+                int j0[kRB], j1[kRB];
+                int64_t row[kRB];
+                float4 w[kRB], m[kRB], v[kRB], acc[kRB];
+                int maxlen = 0;
+#pragma unroll
+                for (int k = 0; k < kRB; ++k) {
+                    const int u = u0 + k;
+                    j0[k] = j1[k] = 0;
+                    row[k] = -1;
+                    if (u < nu) {
+                        j0[k] = heads[u];
+                        j1[k] = (u + 1 < nu) ? heads[u + 1] : cnt;
+                        if (j1[k] - j0[k] >= kLong) {           // deferred to the cooperative path
+                            if (sub == 0) {
+                                const int q = atomicAdd(&sh_nlong, 1);
+                                if (q < 64) longs[q] = (unsigned short)u;
+                            }
+                            j1[k] = j0[k];
+                        } else {
+                            row[k] = (int64_t)(s[j0[k]] >> 32);
+                            maxlen = max(maxlen, j1[k] - j0[k]);
+                        }
                     }
-                    continue;
+                    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row[k] >= 0) {
+                        if (MODE == 2) {
+                            w[k] = ld4(W + row[k] * D + sub * 4);
+                            if (opt.kind == 1) m[k] = ld4(M + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+                            if (opt.kind != 0) v[k] = ld4(V + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+                        } else {
+                            w[k] = ld4(dense + row[k] * D + sub * 4);
+                        }
+                    }
                 }
-                const int64_t row = (int64_t)(s[j0] >> 32);
-                float4 w, m, v;
-                if (MODE == 2) {
-                    w = ld4(W + row * D + sub * 4);
-                    if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                    if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                } else {
-                    w = ld4(dense + row * D + sub * 4);
+                for (int t = 0; t < maxlen; ++t) {
+#pragma unroll
+                    for (int k = 0; k < kRB; ++k) {
+                        if (j0[k] + t < j1[k]) {
+                            const float* base;
+                            int ld;
+                            int64_t r;
+                            float c;
+                            b_contribution(s0, s1, (uint32_t)s[j0[k] + t], base, ld, r, c);
+                            fma4(acc[k], c, ld4(base + r * ld + sub * 4));
+                        }
+                    }
                 }
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int j = j0; j < j1; ++j) {
-                    const float* base;
-                    int ld;
-                    int64_t r;
-                    float c;
-                    b_contribution(s0, s1, (uint32_t)s[j], base, ld, r, c);
-                    fma4(acc, c, ld4(base + r * ld + sub * 4));
-                }
-                RowIO<LPR>::template finish<MODE>(row, acc, sub, w, m, v, W, M, V, dense, opt);
+#pragma unroll
+                for (int k = 0; k < kRB; ++k)
+                    if (row[k] >= 0) RowIO<LPR>::template finish<MODE>(row[k], acc[k], sub, w[k], m[k], v[k], W, M, V, dense, opt);
             }
             __syncthreads();
             // ---- long rows: the whole CTA reduces one row at a time ----------------------------
@@ -476,7 +500,8 @@ struct BucketGeom {
 };
 
 static BucketGeom bucket_geom(int64_t n, int64_t n_rows) {
-    int64_t target = n / 192;                      // ~192 pairs per bucket
+    int64_t target = n / 192;                      // ~192 pairs per bucket ...
+    if (target < 256) target = n / 32;             // ... but at least a few hundred buckets for small batches
     if (target < 1) target = 1;
     if (target > 32768) target = 32768;
     int64_t rows_per = (n_rows + target - 1) / target;
@@ -501,8 +526,8 @@ static BucketLayout bucket_layout(int64_t n, int64_t n_rows) {
         o += align_up(bytes, 256);
         return r;
     };
-    L.count = take((size_t)g.nb * 4);
-    L.cursor = take((size_t)g.nb * 4);
+    L.count = take((size_t)g.nb * 4 * kPad);
+    L.cursor = take((size_t)g.nb * 4 * kPad);
     L.off = take((size_t)(g.nb + 1) * 4);
     L.pairs = take((size_t)n * 8);
     L.total = o;

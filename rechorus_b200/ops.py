@@ -126,6 +126,19 @@ def gather_rows(T: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pairdot(Q: torch.Tensor, qidx: torch.Tensor, T: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """out[e] = <Q[qidx[e]], T[rows[e]]>, rows[e] < 0 -> 0   (b2r_pairdot_fwd; sharded-table owner side)"""
+    _need_cuda(Q, T, qidx, rows)
+    Q, T = _f32c(Q, "Q"), _f32c(T, "T")
+    qidx, rows = _i64c(qidx.reshape(-1), "qidx"), _i64c(rows.reshape(-1), "rows")
+    n = rows.numel()
+    out = torch.empty(n, dtype=torch.float32, device=T.device)
+    L = _lib.load()
+    _lib.check(L.b2r_pairdot_fwd(_p(Q), _p(qidx), Q.shape[0], _p(T), _p(rows), T.shape[0], _p(out), n, T.shape[1],
+                                 _p(err_flag(T.device)), _stream()), "b2r_pairdot_fwd")
+    return out
+
+
 def bpr_loss_and_grad(pred: torch.Tensor, want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """BaseModel.py:175-189 value and closed-form d loss / d pred in one pass."""
     _need_cuda(pred)

@@ -119,6 +119,13 @@ class BPRMFKernels(_KernelModelMixin):
         Needs ``self.optimizer`` to be a ``RowSparseOptimizer``.  ``next_feed_dict`` (optional) is the next
         batch, already on the device: its index plan is prefetched while this step runs.  Returns the loss as a
         device scalar."""
+        if self.emb_size not in (32, 64, 128):
+            # no bucket/fused kernel variant for this width: same step through the autograd nodes
+            self.optimizer.zero_grad()
+            loss = self.loss(self.forward(feed_dict))
+            loss.backward()
+            self.optimizer.step()
+            return loss.detach()
         nu = ni = None
         if next_feed_dict is not None:
             nu, ni = next_feed_dict["user_id"], next_feed_dict["item_id"]

@@ -1,0 +1,210 @@
+"""Row-range sharded BPRMF tables across the GPUs of one box (BASELINE config 5) -- *score routing*.
+
+The reference is single-device (no collectives anywhere); this module is new.  It applies
+only where a table does not fit one GPU with its optimizer state (100 M x 128 fp32 + Adam = 154 GB); configs 1-4
+are replicas-only and never come here.
+
+Per step every rank holds a local batch (user_id [B], item_id [B, C], GLOBAL ids) and owns rows
+``[rank*rows, (rank+1)*rows)`` of each table.  One exchange per direction, NCCL all-to-all over NVLink:
+
+  fwd  user ids -> owners, user vectors back (B x d, small)            all_to_all x2
+       all-gather of the B user vectors (W*B x d, a few MB)            all_gather
+       (sample, local row) pairs bucketed by owner                     all_to_all
+       owners score their pairs against the gathered user vectors
+       (b2r_pairdot_fwd) and return 4-byte scores                      all_to_all
+  bwd  home: BPR loss + gradient g; g -> owners                        all_to_all
+       owners: dQ partials (bucketed dense add) and the fused row-sparse optimizer on their item shard
+       reduce-scatter of the dQ partials to the home ranks             reduce_scatter
+       dQ rows -> user-row owners, fused optimizer on the user shard   all_to_all
+
+Routing 4-byte scores instead of 4d-byte rows keeps the exchange at ~30 MB per rank per step at config-5 sizes
+(vector routing would move ~1 GB and be NVLink-bound), so the step stays HBM-bound on the
+owners' gather / optimizer kernels.  Exchange buffers have a fixed per-destination capacity
+(``cap_factor`` x the uniform share) so that no host synchronisation is needed to size them; a batch whose ids
+overflow a destination trips a device-side assert.
+
+The global objective is the mean BPR loss over the W*B samples of the step (each rank's local mean / W).
+
+All arithmetic goes through a *backend*: ``CudaBackend`` (the sm_100a kernels; the product) -- the tests inject a
+CPU stand-in to exercise the exchange bookkeeping under gloo.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+class CudaBackend:
+    """local compute on the library kernels (rechorus_b200.ops); no CPU fallback"""
+
+    def gather_rows(self, T, ids):
+        from . import ops
+        return ops.gather_rows(T, ids)
+
+    def pairdot(self, Q, qidx, T, rows):
+        from . import ops
+        return ops.pairdot(Q, qidx, T, rows)
+
+    def bpr_loss_and_grad(self, pred):
+        from . import ops
+        return ops.bpr_loss_and_grad(pred)
+
+    def add_rows(self, dense, ids, src, coef, src_id):
+        """dense[ids[p]] += coef[p] * src[src_id[p]] for ids[p] >= 0 (deterministic)"""
+        from . import ops
+        n = ids.numel()
+        plan = ops.make_plan(ids, dense.shape[0], dense.shape[1], ignore_id=-1, ignore_n=n)
+        plan.add_to_dense(dense, [ops.Source(src=src, n=n, coef=coef, src_id=src_id)])
+
+    def optimizer_rows(self, W, state, ids, src, coef, src_id, opt):
+        """row-sparse optimizer on W for the rows ids[p] >= 0 with gradient sum_p coef[p] * src[src_id[p]]"""
+        from . import ops
+        n = ids.numel()
+        plan = ops.make_plan(ids, W.shape[0], W.shape[1], ignore_id=-1, ignore_n=n)
+        plan.apply_optimizer(W, state.get("m"), state.get("v"), opt, [ops.Source(src=src, n=n, coef=coef, src_id=src_id)])
+
+    def make_opt(self, name, lr, betas, eps, wd, t):
+        from . import lib
+        kind = {"SGD": lib.OPT_SGD, "Adam": lib.OPT_ADAM, "Adagrad": lib.OPT_ADAGRAD}[name]
+        return lib.Optim(kind, lr, betas[0], betas[1], eps, wd, 1.0 - betas[0] ** t, 1.0 - betas[1] ** t, 0)
+
+
+def _bucket_by_owner(owner: torch.Tensor, world: int):
+    """stable partition of positions by owner: returns (order, owner_sorted, rank_within_owner, counts)"""
+    order = torch.argsort(owner, stable=True)
+    owner_sorted = owner[order]
+    counts = torch.bincount(owner, minlength=world)
+    starts = torch.cumsum(counts, 0) - counts
+    rank = torch.arange(owner.numel(), device=owner.device) - starts[owner_sorted]
+    return order, owner_sorted, rank, counts
+
+
+class ShardedBPRMF:
+    def __init__(self, n_users: int, n_items: int, d: int, device, backend=None, group=None, optimizer: str = "Adam",
+                 lr: float = 1e-3, l2: float = 0.0, betas=(0.9, 0.999), eps: Optional[float] = None,
+                 cap_factor: float = 1.25, seed: int = 0, init_std: float = 0.01):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_users, self.n_items, self.d, self.device = n_users, n_items, d, device
+        self.rows_u = math.ceil(n_users / self.world)
+        self.rows_i = math.ceil(n_items / self.world)
+        self.backend = backend or CudaBackend()
+        self.opt_name, self.lr, self.l2, self.betas = optimizer, lr, l2, betas
+        self.eps = {"SGD": 0.0, "Adam": 1e-8, "Adagrad": 1e-10}[optimizer] if eps is None else eps
+        self.cap_factor = cap_factor
+        self.t = 0
+        g = torch.Generator(device=device).manual_seed(seed * 1000 + self.rank)
+        # models/BaseModel.py:29-35 init, one shard per rank
+        self.U = torch.randn(self.rows_u, d, device=device, generator=g) * init_std
+        self.I = torch.randn(self.rows_i, d, device=device, generator=g) * init_std
+        self.state_u, self.state_i = {}, {}
+        for st, W in ((self.state_u, self.U), (self.state_i, self.I)):
+            if optimizer == "Adam":
+                st["m"] = torch.zeros_like(W)
+            if optimizer != "SGD":
+                st["v"] = torch.zeros_like(W)
+
+    # -- collectives (degenerate to copies for a single rank) --------------------------------------------
+    def _a2a(self, x: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return x.clone()
+        out = torch.empty_like(x)
+        dist.all_to_all_single(out, x.contiguous(), group=self.group)
+        return out
+
+    def _all_gather(self, x: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return x.clone()
+        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=self.group)
+        return out
+
+    def _reduce_scatter(self, x: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return x.clone()
+        out = torch.empty((x.shape[0] // self.world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def capacity(self, n: int) -> int:
+        if self.world == 1:
+            return n
+        return min(n, int(math.ceil(n / self.world * self.cap_factor)) + 64)
+
+    # -- one training step ----------------------------------------------------------------------------
+    def scores(self, uid: torch.Tensor, iid: torch.Tensor):
+        """forward only: returns (pred [B,C], routing state for the backward)"""
+        W, B, d, be = self.world, uid.numel(), self.d, self.backend
+        C = iid.shape[1]
+        n = B * C
+        dev = uid.device
+        # A. user vectors from their owners
+        own_u = torch.div(uid, self.rows_u, rounding_mode="floor")
+        ord_u, own_us, rank_u, _ = _bucket_by_owner(own_u, W)
+        send_uid = torch.full((W, B), -1, dtype=torch.int64, device=dev)
+        send_uid[own_us, rank_u] = (uid - own_u * self.rows_u)[ord_u]
+        recv_uid = self._a2a(send_uid)                                           # [W(src), B] local rows or -1
+        vec_recv = self._a2a(be.gather_rows(self.U, recv_uid.clamp(min=0)))       # [W(owner), B, d]
+        slot_u = torch.empty(B, dtype=torch.int64, device=dev)
+        slot_u[ord_u] = own_us * B + rank_u                                       # where sample b's vector landed
+        q = be.gather_rows(vec_recv.view(W * B, d), slot_u)                       # [B, d]
+        # B. every owner needs every sample's user vector
+        q_all = self._all_gather(q)                                               # [W*B, d], row = src*B + b
+        # C. (sample, local row) pairs to the item-row owners, fixed capacity per destination
+        flat = iid.reshape(-1)
+        own_i = torch.div(flat, self.rows_i, rounding_mode="floor")
+        ord_i, own_is, rank_i, counts_i = _bucket_by_owner(own_i, W)
+        cap = self.capacity(n)
+        torch._assert_async(counts_i.max() <= cap)                                # ids too skewed for cap_factor
+        send_pairs = torch.full((W, cap, 2), -1, dtype=torch.int64, device=dev)
+        keep_rank = rank_i.clamp(max=cap - 1)
+        send_pairs[own_is, keep_rank, 0] = (flat - own_i * self.rows_i)[ord_i]
+        send_pairs[own_is, keep_rank, 1] = torch.div(ord_i, C, rounding_mode="floor")
+        recv_pairs = self._a2a(send_pairs)                                        # [W(src), cap, 2]
+        rows = recv_pairs[:, :, 0].contiguous()
+        src_base = (torch.arange(W, device=dev) * B).view(W, 1)
+        qidx = (recv_pairs[:, :, 1].clamp(min=0) + src_base).contiguous()         # row of q_all
+        # D. owners score, scores travel back
+        sc_recv = self._a2a(be.pairdot(q_all, qidx, self.I, rows).view(W, cap))   # [W(owner), cap]
+        pred = torch.empty(n, dtype=torch.float32, device=dev)
+        pred[ord_i] = sc_recv[own_is, keep_rank]
+        state = dict(B=B, C=C, n=n, cap=cap, ord_u=ord_u, own_us=own_us, rank_u=rank_u, recv_uid=recv_uid,
+                     ord_i=ord_i, own_is=own_is, keep_rank=keep_rank, rows=rows, qidx=qidx, q_all=q_all)
+        return pred.view(B, C), state
+
+    def train_step(self, uid: torch.Tensor, iid: torch.Tensor) -> torch.Tensor:
+        W, d, be = self.world, self.d, self.backend
+        pred, st = self.scores(uid, iid)
+        B, C, cap = st["B"], st["C"], st["cap"]
+        dev = uid.device
+        # E. local loss; the step's objective is the mean over the W*B global samples
+        loss, g = be.bpr_loss_and_grad(pred)
+        g = g / W
+        # F. g to the owners, in the order the pairs were sent
+        g_send = torch.zeros((W, cap), dtype=torch.float32, device=dev)
+        g_send[st["own_is"], st["keep_rank"]] = g.reshape(-1)[st["ord_i"]]
+        g_recv = self._a2a(g_send).reshape(-1)                                    # [W*cap], 0 in unused slots
+        rows, qidx, q_all = st["rows"].reshape(-1), st["qidx"].reshape(-1), st["q_all"]
+        valid_rows = rows.clamp(min=0)
+        self.t += 1
+        opt_i = be.make_opt(self.opt_name, self.lr, self.betas, self.eps, self.l2, self.t)
+        # G. dQ partials for every (src, sample) this owner served: dQ[src*B+b] += g * I[row]   (before I moves)
+        dq_part = torch.zeros((W * B, d), dtype=torch.float32, device=dev)
+        be.add_rows(dq_part, torch.where(rows >= 0, qidx, torch.full_like(qidx, -1)), self.I, g_recv, valid_rows)
+        # H. item shard: fused row-sparse optimizer, gradient row = sum g * q_all[qidx]
+        be.optimizer_rows(self.I, self.state_i, rows, q_all, g_recv, qidx, opt_i)
+        # I. home ranks get their samples' dQ summed over the owners
+        dq = self._reduce_scatter(dq_part)                                        # [B, d]
+        # J. dQ rows to the user-row owners, fused optimizer on the user shard
+        dq_send = torch.zeros((W, B, d), dtype=torch.float32, device=dev)
+        dq_send[st["own_us"], st["rank_u"]] = dq[st["ord_u"]]
+        dq_recv = self._a2a(dq_send).view(W * B, d)
+        recv_uid = st["recv_uid"].reshape(-1)
+        ar = torch.arange(W * B, device=dev)
+        be.optimizer_rows(self.U, self.state_u, recv_uid, dq_recv, torch.ones(W * B, dtype=torch.float32, device=dev),
+                          ar, opt_i)
+        return loss
