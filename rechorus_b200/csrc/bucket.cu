@@ -10,6 +10,8 @@
 // larger than the shared-memory capacity are walked row by row in position ranges -- both keep the result
 // independent of scheduling.  Replaces ATen embedding_dense_backward + the dense grad zero-fill + the embedding
 // part of optimizer.step() (helpers/BaseRunner.py:193,205,206).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2r {
@@ -27,7 +29,6 @@ constexpr int kCap = 2048;        // pairs a CTA sorts in shared memory (16 KB)
 constexpr int kLong = 48;         // rows with at least this many contributions are reduced by the whole CTA
 constexpr int kBT = 256;
 constexpr int kPad = 32;          // ints per bucket counter: one 128-byte line each (L2 atomics serialise per line)
-constexpr int kRB = 4;            // unique rows a lane group keeps in flight in k_bucket_apply
 
 __device__ __forceinline__ void b_contribution(const BSrc& s0, const BSrc& s1, uint32_t p, const float*& base,
                                                int& ld, int64_t& row, float& c) {
@@ -36,7 +37,7 @@ __device__ __forceinline__ void b_contribution(const BSrc& s0, const BSrc& s1, u
     const int div = first ? s0.div : s1.div;
     const int64_t* sid = first ? s0.src_id : s1.src_id;
     const float* cf = first ? s0.coef : s1.coef;
-    int64_t r = (div == 1) ? pp : pp / div;
+    int64_t r = (div == 1) ? pp : (int64_t)((uint32_t)pp / (uint32_t)div);
     if (sid != nullptr) r = sid[r];
     row = r;
     c = (cf != nullptr) ? cf[pp] : 1.f;
@@ -143,12 +144,12 @@ struct RowIO {
     // MODE 0: rows -> grad_rows[out_base + u], uniq_rows; MODE 1: dense += ; MODE 2: optimizer in place
     template <int MODE>
     __device__ static __forceinline__ void finish(int64_t row, const float4& acc, int sub, float4 w, float4 m, float4 v,
-                                                  float* W, float* M, float* V, float* dense, const b2r_optim& opt) {
+                                                  float* W, float* M, float* V, float* dense, const OptK& opt) {
         if (MODE == 1) {
             w.x += acc.x; w.y += acc.y; w.z += acc.z; w.w += acc.w;
             st4(dense + row * D + sub * 4, w);
         } else {
-            b_optim(opt, w, m, v, acc);
+            optk_update4(opt, w, m, v, acc);
             st4(W + row * D + sub * 4, w);
             if (opt.kind == 1) st4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4, m);
             if (opt.kind != 0) st4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4, v);
@@ -174,11 +175,12 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, int P) {
     }
 }
 
-template <int LPR, int MODE>
-__global__ void __launch_bounds__(kBT, 2)
+// kRB = unique rows a lane group keeps in flight
+template <int LPR, int MODE, int kRB>
+__global__ void __launch_bounds__(kBT, (kRB <= 2) ? 3 : 2)
 k_bucket_apply(const uint64_t* __restrict__ pairs, const int* __restrict__ off, int nb, BSrc s0, BSrc s1,
                float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense,
-               b2r_optim opt) {
+               OptK opt) {
     constexpr int D = LPR * 4;
     constexpr int GPC = kBT / LPR;
     __shared__ uint64_t s[kCap];
@@ -382,7 +384,7 @@ template <int LPR, int MODE>
 __global__ void __launch_bounds__(kBT)
 k_bucket_apply_big(const uint64_t* __restrict__ pairs, const int* __restrict__ off, int nb, BSrc s0, BSrc s1,
                    float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense,
-                   b2r_optim opt) {
+                   OptK opt) {
     constexpr int D = LPR * 4;
     constexpr int GPC = kBT / LPR;
     __shared__ uint64_t s[kCap];
@@ -625,10 +627,19 @@ extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d
     const int cap = sm_count() * 8;
     const int grid = g.nb < cap ? g.nb : cap;
     const int big_grid = g.nb < sm_count() ? g.nb : sm_count();
+    const OptK ok = make_optk(o);
+    static int rb = -1;                    // tuning knob B2R_BUCKET_RB = 1 | 2 | 4 (read once)
+    if (rb < 0) {
+        const char* e = getenv("B2R_BUCKET_RB");
+        rb = e ? atoi(e) : 2;
+        if (rb != 1 && rb != 2 && rb != 4) rb = 2;
+    }
 #define B2R_BK(LPR, MODE)                                                                              \
     do {                                                                                               \
-        k_bucket_apply<LPR, MODE><<<grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, o);     \
-        k_bucket_apply_big<LPR, MODE><<<big_grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, o); \
+        if (rb == 1) k_bucket_apply<LPR, MODE, 1><<<grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, ok); \
+        else if (rb == 2) k_bucket_apply<LPR, MODE, 2><<<grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, ok); \
+        else k_bucket_apply<LPR, MODE, 4><<<grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, ok); \
+        k_bucket_apply_big<LPR, MODE><<<big_grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, ok); \
     } while (0)
     if (mode == 1) {
         if (d == 32) B2R_BK(8, 1); else if (d == 64) B2R_BK(16, 1); else B2R_BK(32, 1);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <math.h>
 
 #include "../../include/b200rec.h"
 
@@ -97,6 +98,54 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(B2R_FULL_MASK, v, o));
     return v;
+}
+
+// Optimizer constants precomputed once on the host in double precision (1 - beta as torch computes it, the
+// step size lr / bias_correction1 and 1 / sqrt(bias_correction2)) so that the per-element update costs one sqrt
+// and one division instead of two square roots and three divisions.
+struct OptK {
+    int kind;          // 0 SGD, 1 Adam, 2 Adagrad
+    int state_ld;
+    float lr, beta1, beta2, eps, wd, omb1, omb2, step, isb2;
+};
+
+static inline OptK make_optk(const b2r_optim& o) {
+    OptK k;
+    k.kind = o.kind;
+    k.state_ld = o.state_ld;
+    k.lr = o.lr;
+    k.beta1 = o.beta1;
+    k.beta2 = o.beta2;
+    k.eps = o.eps;
+    k.wd = o.weight_decay;
+    k.omb1 = (float)(1.0 - (double)o.beta1);
+    k.omb2 = (float)(1.0 - (double)o.beta2);
+    k.step = (o.kind == 1 && o.bc1 != 0.f) ? (float)((double)o.lr / (double)o.bc1) : o.lr;
+    k.isb2 = (o.kind == 1 && o.bc2 > 0.f) ? (float)(1.0 / sqrt((double)o.bc2)) : 1.f;
+    return k;
+}
+
+// one element of torch.optim.{SGD, Adam (amsgrad off), Adagrad}.step() with coupled L2 (g += wd * w)
+__device__ __forceinline__ void optk_elem(const OptK& o, float& w, float& m, float& v, float gin) {
+    const float g = fmaf(o.wd, w, gin);
+    if (o.kind == 0) {
+        w = fmaf(-o.lr, g, w);
+    } else if (o.kind == 1) {
+        m = fmaf(o.beta1, m, o.omb1 * g);
+        v = fmaf(o.beta2, v, o.omb2 * g * g);
+        const float denom = fmaf(sqrtf(v), o.isb2, o.eps);
+        w = fmaf(-o.step, m / denom, w);
+    } else {
+        v = fmaf(g, g, v);
+        w = fmaf(-o.lr, g / (sqrtf(v) + o.eps), w);
+    }
+}
+
+__device__ __forceinline__ void optk_update4(const OptK& o, float4& w, float4& m, float4& v, const float4& g) {
+    optk_elem(o, w.x, m.x, v.x, g.x);
+    optk_elem(o, w.y, m.y, v.y, g.y);
+    optk_elem(o, w.z, m.z, v.z, g.z);
+    optk_elem(o, w.w, m.w, v.w, g.w);
 }
 
 // id range check: clamp to row 0 and count the violation (reference: ATen index error)

@@ -26,7 +26,7 @@ __device__ __forceinline__ void contribution(const Src& s0, const Src& s1, uint3
     const bool first = (int64_t)p < s0.n;
     const Src& s = first ? s0 : s1;   // (references to kernel params: resolved by predication)
     const int64_t pp = first ? (int64_t)p : (int64_t)p - s0.n;
-    int64_t r = (s.div == 1) ? pp : pp / s.div;
+    int64_t r = (s.div == 1) ? pp : (int64_t)((uint32_t)pp / (uint32_t)s.div);
     if (s.src_id != nullptr) r = s.src_id[r];
     row = r;
     c = (s.coef != nullptr) ? s.coef[pp] : 1.f;
@@ -60,7 +60,7 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
                 const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n, int64_t n_rows,
                 Src s0, Src s1, int64_t* __restrict__ uniq_rows, float* __restrict__ grad_rows,
                 float* __restrict__ dense, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V,
-                b2r_optim opt) {
+                OptK opt) {
     constexpr int D = LPR * 4;
     constexpr int GPC = 256 / LPR;
     const int sub = threadIdx.x % LPR;
@@ -97,7 +97,7 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
             w.x += acc.x; w.y += acc.y; w.z += acc.z; w.w += acc.w;
             st4(dense + row * D + sub * 4, w);
         } else {
-            optim_update(opt, w, m, v, acc);
+            optk_update4(opt, w, m, v, acc);
             st4(W + row * D + sub * 4, w);
             if (opt.kind == 1) st4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4, m);
             if (opt.kind != 0) st4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4, v);
@@ -113,7 +113,7 @@ template <int LPR, int RPI>
 __global__ void __launch_bounds__(256)
 k_segment_optim(const uint32_t* __restrict__ sorted_key, const uint32_t* __restrict__ sorted_pos,
                 const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n, int64_t n_rows,
-                Src s0, Src s1, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, b2r_optim opt) {
+                Src s0, Src s1, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, OptK opt) {
     static_assert(RPI < LPR, "segment bounds are loaded one per lane");
     constexpr int D = LPR * 4;
     constexpr int GPC = 256 / LPR;
@@ -175,7 +175,7 @@ k_segment_optim(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
 #pragma unroll
         for (int k = 0; k < RPI; ++k) {
             if (row[k] < n_rows) {
-                optim_update(opt, w[k], m[k], v[k], acc[k]);
+                optk_update4(opt, w[k], m[k], v[k], acc[k]);
                 st4(W + row[k] * D + sub * 4, w[k]);
                 if (opt.kind == 1) st4(M + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4, m[k]);
                 if (opt.kind != 0) st4(V + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4, v[k]);
@@ -191,7 +191,7 @@ k_segment_apply_generic(const uint32_t* __restrict__ sorted_key, const uint32_t*
                         const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n,
                         int64_t n_rows, int d, Src s0, Src s1, int64_t* __restrict__ uniq_rows, float* __restrict__ grad_rows,
                         float* __restrict__ dense, float* __restrict__ W, float* __restrict__ M,
-                        float* __restrict__ V, b2r_optim opt) {
+                        float* __restrict__ V, OptK opt) {
     const int lane = threadIdx.x & 31;
     const int nu = *n_uniq;
     const int d4 = d >> 2;
@@ -220,7 +220,7 @@ k_segment_apply_generic(const uint32_t* __restrict__ sorted_key, const uint32_t*
                 float4 w = ld4(W + row * d + k * 4), m, v;
                 if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : d) + k * 4);
                 if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : d) + k * 4);
-                optim_update(opt, w, m, v, acc);
+                optk_update4(opt, w, m, v, acc);
                 st4(W + row * d + k * 4, w);
                 if (opt.kind == 1) st4(M + row * (opt.state_ld ? opt.state_ld : d) + k * 4, m);
                 if (opt.kind != 0) st4(V + row * (opt.state_ld ? opt.state_ld : d) + k * 4, v);
@@ -252,14 +252,14 @@ k_scatter_add_atomic(const int64_t* __restrict__ ids, int64_t n_rows, Src s, int
 
 __global__ void __launch_bounds__(256)
 k_dense_optim(float* __restrict__ W, const float* __restrict__ G, float* __restrict__ M, float* __restrict__ V,
-              int64_t numel, b2r_optim opt) {
+              int64_t numel, OptK opt) {
     const int64_t n4 = numel >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 w = ld4(W + i * 4), m, v;
         const float4 g = ld4(G + i * 4);
         if (opt.kind == 1) m = ld4(M + i * 4);
         if (opt.kind != 0) v = ld4(V + i * 4);
-        optim_update(opt, w, m, v, g);
+        optk_update4(opt, w, m, v, g);
         st4(W + i * 4, w);
         if (opt.kind == 1) st4(M + i * 4, m);
         if (opt.kind != 0) st4(V + i * 4, v);
@@ -270,7 +270,7 @@ k_dense_optim(float* __restrict__ W, const float* __restrict__ G, float* __restr
         float4 w = make_float4(W[i], 0, 0, 0), m = make_float4(0, 0, 0, 0), v = make_float4(0, 0, 0, 0);
         if (opt.kind == 1) m.x = M[i];
         if (opt.kind != 0) v.x = V[i];
-        optim_update(opt, w, m, v, make_float4(G[i], 0, 0, 0));
+        optk_update4(opt, w, m, v, make_float4(G[i], 0, 0, 0));
         W[i] = w.x;
         if (opt.kind == 1) M[i] = m.x;
         if (opt.kind != 0) V[i] = v.x;
@@ -333,7 +333,7 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
         const int64_t cap = (int64_t)sm_count() * 16;                                                  \
         const int grid = (int)(need < cap ? need : cap);                                               \
         k_segment_apply<LPR, MODE><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, n_rows, a, b, \
-                                                        uniq_rows, grad_rows, dense, W, m, v, o);      \
+                                                        uniq_rows, grad_rows, dense, W, m, v, make_optk(o)); \
     } while (0)
 #define B2R_SEG_D(MODE)                                                                                \
     do {                                                                                               \
@@ -345,7 +345,7 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
             const int64_t cap = (int64_t)sm_count() * 16;                                              \
             const int grid = (int)(need < cap ? need : cap);                                           \
             k_segment_apply_generic<MODE><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, n_rows, d, \
-                                                               a, b, uniq_rows, grad_rows, dense, W, m, v, o); \
+                                                               a, b, uniq_rows, grad_rows, dense, W, m, v, make_optk(o)); \
         }                                                                                              \
     } while (0)
     static int rpi = -1;                 // tuning knob (B2R_SEG_RPI = 0 | 1 | 2 | 4), read once; 0 = one-row kernel
@@ -361,7 +361,7 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
         const int64_t cap = (int64_t)sm_count() * 16;                                                  \
         const int grid = (int)(need < cap ? need : cap);                                               \
         k_segment_optim<LPR, RPI><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, n_rows, a, b, \
-                                                       W, m, v, o);                                    \
+                                                       W, m, v, make_optk(o));                         \
     } while (0)
 #define B2R_OPT_R(LPR)                                                                                 \
     do {                                                                                               \
@@ -407,7 +407,7 @@ extern "C" int b2r_dense_optim(float* W, const float* grad, float* m, float* v, 
     int64_t need = ((numel >> 2) + 255) / 256;
     if (need < 1) need = 1;
     const int64_t cap = (int64_t)sm_count() * 16;
-    k_dense_optim<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(W, grad, m, v, numel, *opt);
+    k_dense_optim<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(W, grad, m, v, numel, make_optk(*opt));
     B2R_LAUNCH_OK("k_dense_optim");
     return 0;
 }

@@ -99,8 +99,8 @@ class ShardedBPRMF:
         self.t = 0
         g = torch.Generator(device=device).manual_seed(seed * 1000 + self.rank)
         # models/BaseModel.py:29-35 init, one shard per rank
-        self.U = torch.randn(self.rows_u, d, device=device, generator=g) * init_std
-        self.I = torch.randn(self.rows_i, d, device=device, generator=g) * init_std
+        self.U = torch.empty(self.rows_u, d, device=device).normal_(0.0, init_std, generator=g)
+        self.I = torch.empty(self.rows_i, d, device=device).normal_(0.0, init_std, generator=g)
         self.state_u, self.state_i = {}, {}
         for st, W in ((self.state_u, self.U), (self.state_i, self.I)):
             if optimizer == "Adam":
