@@ -24,17 +24,20 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
-// A CTA walks passes p = blockIdx.x, += gridDim.x; a pass covers SPB = GPC/GPS samples.  The candidate rows of
-// pass p+1 are requested (second register set) before pass p enters its barrier phases, so HBM latency overlaps
-// the loss/gradient arithmetic and the three barriers of the current pass.  Phases of a pass:
-//   rows -> scores (shared memory)  |barrier|  one WARP per sample: softmax/sigmoid statistics and the gradient g of
-//   every candidate, each transcendental evaluated once  |barrier|  lane groups: acc = sum g*row  |barrier|
-//   ordered combine of the GPS partials -> dQ.   Shared buffers alternate by pass parity (no trailing barrier).
+// A CTA walks passes p = blockIdx.x, += gridDim.x; a pass covers SPB = GPC/GPS samples.  Software pipeline, two
+// deep: while pass p is being reduced, the candidate rows of pass p+1 are in flight (second register set) and the
+// ids of pass p+2 are in flight (one register), so neither the id fetch nor the row fetch latency is exposed.
+// Phases of a pass (every thread works in every phase; each transcendental is evaluated once per candidate):
+//   dots: lane k of a group ends up holding the score of the group's k-th row
+//   A: per-sample max over the negatives          warp shuffle + shared memory, |barrier|
+//   B: e = exp(x-max), s = sigmoid(p-x) for the thread's own candidate; per-sample sums Z, A, D  |barrier|
+//   C: g for the own candidate (stored), broadcast inside the group, acc = sum g*row -> shared memory  |barrier|
+//   D: 4*LPR threads per sample add the GPS partials in group order -> dQ (deterministic)
+// Shared buffers alternate by pass parity, so no barrier is needed between passes.
 template <int LPR, int RPG>
 struct FusedPass {
     static constexpr int D = LPR * 4;
     static constexpr int GPC = 256 / LPR;
-    static constexpr int CPL = (GPC * RPG + 31) / 32;      // candidates per lane in the statistics warp
 
     const float* U; const int64_t* uid; int64_t n_users;
     const float* T; const int64_t* ids; int64_t n_t;
@@ -43,15 +46,20 @@ struct FusedPass {
     int sub, grp, lane, warp, SPB, j, slot, c_mine;
     float invB;
 
-    __device__ __forceinline__ void load(int64_t pass, float4 (&r)[RPG], float4& q) const {
+    __device__ __forceinline__ int64_t load_id(int64_t pass) const {
+        const int64_t b = pass * SPB + slot;
+        int64_t my_id = 0;
+        if (b < B && sub < RPG && c_mine < C) my_id = ids[b * C + c_mine];
+        return my_id;
+    }
+
+    __device__ __forceinline__ void load_rows(int64_t pass, int64_t my_id_raw, float4 (&r)[RPG], float4& q) const {
         const int64_t b = pass * SPB + slot;
         const bool have = b < B;
-        const bool mine_ok = have && sub < RPG && c_mine < C;
         int64_t qrow = 0;
         if (have) qrow = checked_id(uid[b], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
         q = ld4(U + qrow * D + sub * 4);
-        int64_t my_id = 0;
-        if (mine_ok) my_id = checked_id(ids[b * C + c_mine], n_t, err_flag);
+        const int64_t my_id = checked_id(my_id_raw, n_t, err_flag);
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
             const int64_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
@@ -60,93 +68,81 @@ struct FusedPass {
         }
     }
 
-    __device__ __forceinline__ void compute(int64_t pass, const float4 (&r)[RPG], const float4& q, float* sp,
-                                            float4 (*part)[LPR]) const {
-        const int64_t b0 = pass * SPB;
-        const int64_t b = b0 + slot;
+    // sred: [SPB][GPS*?]... per-sample scratch: smx[slot][GPS] maxima, ssum[slot][GPS][3] sums, spos[slot] positive score
+    __device__ __forceinline__ void compute(int64_t pass, const float4 (&r)[RPG], const float4& q, float* smx,
+                                            float* ssum, float* spos, float4 (*part)[LPR]) const {
+        const int64_t b = pass * SPB + slot;
         const bool have = b < B;
-        float mine = 0.f;
+        const bool mine_ok = have && sub < RPG && c_mine < C;
+        float x = 0.f;                                    // score of the candidate this lane speaks for
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
             const float v = group_sum<LPR>(dot4(q, r[k]));
-            if (sub == k) mine = v;
+            if (sub == k) x = v;
         }
-        if (have && sub < RPG && c_mine < C) {
-            sp[slot * (GPS * RPG) + c_mine] = mine;
-            if (pred != nullptr) pred[b * C + c_mine] = mine;
+        if (mine_ok && pred != nullptr) pred[b * C + c_mine] = x;
+        // ---- A: max over this sample's negatives (candidates c >= 1) -------------------------------------
+        const bool is_neg = mine_ok && c_mine > 0;
+        float mx = is_neg ? x : -INFINITY;
+        mx = group_max<LPR>(mx);
+        if (sub == 0) smx[slot * GPS + j] = mx;           // one value per group of the sample
+        if (mine_ok && c_mine == 0) spos[slot] = x;
+        __syncthreads();
+        mx = -INFINITY;
+        for (int t = 0; t < GPS; ++t) mx = fmaxf(mx, smx[slot * GPS + t]);
+        const float p = spos[slot];
+        // ---- B: per-candidate terms, per-sample sums ---------------------------------------------------
+        float e = 0.f, sg = 0.f;
+        if (is_neg) {
+            e = expf(x - mx);
+            sg = sigmoidf_f(p - x);
+        }
+        float Z = group_sum<LPR>(e);
+        float A = group_sum<LPR>(e * sg);
+        float Dp = group_sum<LPR>(e * sg * (1.f - sg));
+        if (sub == 0) {
+            ssum[(slot * GPS + j) * 3 + 0] = Z;
+            ssum[(slot * GPS + j) * 3 + 1] = A;
+            ssum[(slot * GPS + j) * 3 + 2] = Dp;
         }
         __syncthreads();
-        for (int sl = warp; sl < SPB; sl += 8) {                 // warp-uniform
-            const int64_t bb = b0 + sl;
-            if (bb >= B) continue;
-            float* myp = sp + sl * (GPS * RPG);
-            const float p = myp[0];
-            float x[CPL], e[CPL], sg[CPL];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                const int c = 1 + lane + 32 * i;
-                x[i] = (c < C) ? myp[c] : -INFINITY;
-                mx = fmaxf(mx, x[i]);
-            }
-            mx = warp_max(mx);
-            float Z = 0.f, A = 0.f, Dp = 0.f;
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                const int c = 1 + lane + 32 * i;
-                e[i] = 0.f;
-                sg[i] = 0.f;
-                if (c < C) {
-                    e[i] = expf(x[i] - mx);
-                    sg[i] = sigmoidf_f(p - x[i]);
-                    Z += e[i];
-                    A = fmaf(e[i], sg[i], A);
-                    Dp = fmaf(e[i] * sg[i], 1.f - sg[i], Dp);
-                }
-            }
-            Z = warp_sum(Z);
-            A = warp_sum(A);
-            Dp = warp_sum(Dp);
-            const float S = (C > 1) ? A / Z : 0.f;
-            const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
-            const float Sc = fminf(fmaxf(S, 1e-8f), 1.f - 1e-8f);
-            const float dS = inside ? -invB / S : 0.f;
-            const float invZ = (C > 1) ? 1.f / Z : 0.f;
-            __syncwarp();                                        // every lane has read its scores: overwrite with g
-#pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                const int c = 1 + lane + 32 * i;
-                if (c < C) {
-                    const float g = dS * (e[i] * invZ) * ((sg[i] - S) - sg[i] * (1.f - sg[i]));
-                    myp[c] = g;
-                    gout[bb * C + c] = g;
-                }
-            }
-            if (lane == 0) {
-                const float g0 = dS * Dp * invZ;
-                myp[0] = g0;
-                gout[bb * C] = g0;
-                row_loss[bb] = -logf(Sc);
-            }
+        Z = A = Dp = 0.f;
+        for (int t = 0; t < GPS; ++t) {                   // fixed order
+            Z += ssum[(slot * GPS + t) * 3 + 0];
+            A += ssum[(slot * GPS + t) * 3 + 1];
+            Dp += ssum[(slot * GPS + t) * 3 + 2];
         }
-        __syncthreads();
-        const float* myg = sp + slot * (GPS * RPG);
+        const float S = (C > 1) ? A / Z : 0.f;
+        const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
+        const float dS = inside ? -invB / S : 0.f;
+        const float invZ = (C > 1) ? 1.f / Z : 0.f;
+        // ---- C: gradient of the own candidate, acc = sum_k g_k * row_k ----------------------------------
+        float gmine = 0.f;
+        if (mine_ok) {
+            gmine = (c_mine == 0) ? dS * Dp * invZ : dS * (e * invZ) * ((sg - S) - sg * (1.f - sg));
+            gout[b * C + c_mine] = gmine;
+        }
+        if (have && j == 0 && sub == 0) row_loss[b] = -logf(fminf(fmaxf(S, 1e-8f), 1.f - 1e-8f));
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
-            const int c = j + GPS * k;
-            const float gk = (have && c < C) ? myg[c] : 0.f;
+            const float gk = __shfl_sync(B2R_FULL_MASK, gmine, k, LPR);
             fma4(acc, gk, r[k]);
         }
         part[grp][sub] = acc;
         __syncthreads();
-        if (j == 0 && have) {
-            float4 tot = part[grp][sub];
-            for (int t = 1; t < GPS; ++t) {
-                const float4 y = part[grp + t][sub];
-                tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
+        // ---- D: ordered combine: thread (slot, column) sums the GPS partials of its sample ----------------
+        {
+            const float* pf = reinterpret_cast<const float*>(part);
+            for (int o = threadIdx.x; o < SPB * D; o += 256) {
+                const int sl = o / D, col = o % D;
+                const int64_t bb = pass * SPB + sl;
+                if (bb < B) {
+                    float tot = 0.f;
+                    for (int t = 0; t < GPS; ++t) tot += pf[(sl * GPS + t) * D + col];
+                    dQ[bb * D + col] = tot;
+                }
             }
-            st4(dQ + b * D + sub * 4, tot);
         }
     }
 };
@@ -159,8 +155,10 @@ k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
               float* __restrict__ dQ, int B, int C, int GPS, int32_t* err_flag) {
     static_assert(RPG <= LPR, "ids of a group's rows are loaded one per lane");
     using P = FusedPass<LPR, RPG>;
-    __shared__ float sp[2][P::GPC * RPG];                 // scores, then gradients (alternating by pass parity)
-    __shared__ float4 part[2][P::GPC][LPR];               // partial dQ per group
+    __shared__ float smx[2][P::GPC];
+    __shared__ float ssum[2][P::GPC * 3];
+    __shared__ float spos[2][P::GPC];
+    __shared__ float4 part[2][P::GPC][LPR];               // partial dQ per group (alternating by pass parity)
     P f;
     f.U = U; f.uid = uid; f.n_users = n_users; f.T = T; f.ids = ids; f.n_t = n_t;
     f.pred = pred; f.gout = gout; f.row_loss = row_loss; f.dQ = dQ; f.B = B; f.C = C; f.GPS = GPS; f.err_flag = err_flag;
@@ -169,17 +167,27 @@ k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
     f.SPB = P::GPC / GPS; f.j = f.grp % GPS; f.slot = f.grp / GPS; f.c_mine = f.j + GPS * f.sub;
     f.invB = 1.f / (float)B;
     const int64_t npass = ((int64_t)B + f.SPB - 1) / f.SPB;
+    const int64_t G = gridDim.x;
     float4 ra[RPG], rb[RPG], qa, qb;
     int64_t p = blockIdx.x;
-    if (p < npass) f.load(p, ra, qa);
-    for (; p < npass; p += 2 * (int64_t)gridDim.x) {
-        const int64_t p1 = p + gridDim.x;
-        if (p1 < npass) f.load(p1, rb, qb);               // next pass's rows are in flight during this pass
-        f.compute(p, ra, qa, sp[0], part[0]);
+    int64_t id_nxt = 0;
+    if (p < npass) {
+        f.load_rows(p, f.load_id(p), ra, qa);
+        if (p + G < npass) id_nxt = f.load_id(p + G);
+    }
+    for (; p < npass; p += 2 * G) {
+        const int64_t p1 = p + G, p2 = p + 2 * G, p3 = p + 3 * G;
         if (p1 < npass) {
-            const int64_t p2 = p1 + gridDim.x;
-            if (p2 < npass) f.load(p2, ra, qa);
-            f.compute(p1, rb, qb, sp[1], part[1]);
+            f.load_rows(p1, id_nxt, rb, qb);              // rows of the next pass in flight during this one
+            if (p2 < npass) id_nxt = f.load_id(p2);        // ids of the pass after that
+        }
+        f.compute(p, ra, qa, smx[0], ssum[0], spos[0], part[0]);
+        if (p1 < npass) {
+            if (p2 < npass) {
+                f.load_rows(p2, id_nxt, ra, qa);
+                if (p3 < npass) id_nxt = f.load_id(p3);
+            }
+            f.compute(p1, rb, qb, smx[1], ssum[1], spos[1], part[1]);
         }
     }
 }

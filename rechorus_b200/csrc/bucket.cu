@@ -1,15 +1,21 @@
-// bucket.cu -- the hot-path form of the row-sparse embedding backward + optimizer (K2b):
-//   1. k_bucket_count / k_bucket_scan / k_bucket_scatter: partition the batch's (row id, position) pairs into
-//      buckets of 2^shift consecutive table rows (~200 pairs each) -- two passes over the ids with L2 atomics,
-//      ~10x cheaper than a full device radix sort of the ids;
-//   2. k_bucket_apply: one CTA per bucket loads its pairs into shared memory, sorts them by (row, position)
-//      with a bitonic network, finds the run heads, and its lane groups then own one unique row each: walk the
-//      row's contributions in ascending position (deterministic, whatever order the atomics of step 1 produced),
-//      and apply SGD/Adam/Adagrad to w (m, v) in place -- or emit / accumulate the gradient row.
-// Rows with many contributions are reduced by the whole CTA (fixed assignment + fixed combine order), buckets
-// larger than the shared-memory capacity are walked row by row in position ranges -- both keep the result
-// independent of scheduling.  Replaces ATen embedding_dense_backward + the dense grad zero-fill + the embedding
-// part of optimizer.step() (helpers/BaseRunner.py:193,205,206).
+// bucket.cu -- the hot-path form of the row-sparse embedding backward + optimizer (K2b).
+//   plan side (depends only on the ids; runs on the step context's side stream, one step ahead):
+//     k_bucket_count / k_bucket_scan / k_bucket_scatter  partition the batch's (row id, position) pairs into buckets
+//         of 2^shift consecutive table rows (~200 pairs each): two passes over the ids with L2 atomics on
+//         line-padded counters;
+//     k_bucket_sort  one CTA per bucket sorts its pairs by (row, position) in shared memory (bitonic network) and
+//         writes them back in place.  Buckets cover ascending disjoint row ranges, so the whole array ends up
+//         sorted exactly as a device-wide radix sort would leave it, at a fraction of the cost; rows with many
+//         contributions are listed for the cooperative kernel; buckets beyond the shared-memory capacity are
+//         chunk-sorted and merged.
+//   apply side (main stream):
+//     k_apply_sorted  one lane group per pair; the group holding the first pair of a row owns the row: requests
+//         w (m, v), walks the row's contributions in ascending position, applies SGD/Adam/Adagrad in place (mode 2)
+//         or adds into a dense gradient (mode 1).  No shared memory, no barriers, no atomics.
+//     k_apply_long    rows with >= kLong contributions, reduced by a whole CTA in a fixed order.
+// Every sum has a fixed order whatever order the partition's atomics produced -> same bits on every run.
+// Replaces ATen embedding_dense_backward + the dense grad zero-fill + the embedding part of optimizer.step()
+// (helpers/BaseRunner.py:193,205,206).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -86,12 +92,17 @@ __global__ void __launch_bounds__(1024)
 k_bucket_scan(int* __restrict__ count, int* __restrict__ cursor, int* __restrict__ off, int nb) {
     __shared__ int wsum[32];
     __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ int nbig;
+    if (threadIdx.x == 0) {
+        carry = 0;
+        nbig = 0;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < nb; base += 1024) {
         const int i = base + threadIdx.x;
         const int v = i < nb ? count[(int64_t)i * kPad] : 0;
+        if (v > kCap) atomicAdd(&nbig, 1);
         int x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -120,7 +131,11 @@ k_bucket_scan(int* __restrict__ count, int* __restrict__ cursor, int* __restrict
         if (threadIdx.x == 1023) carry += wsum[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) off[nb] = carry;
+    if (threadIdx.x == 0) {
+        off[nb] = carry;
+        off[nb + 1] = nbig;          // number of buckets too large for the shared-memory sort (informational)
+        off[nb + 2] = 0;             // long-row counter, filled by k_bucket_sort
+    }
 }
 
 __global__ void __launch_bounds__(kBT)
@@ -175,201 +190,92 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* s, int P) {
     }
 }
 
-// kRB = unique rows a lane group keeps in flight
-template <int LPR, int MODE, int kRB>
-__global__ void __launch_bounds__(kBT, (kRB <= 2) ? 3 : 2)
-k_bucket_apply(const uint64_t* __restrict__ pairs, const int* __restrict__ off, int nb, BSrc s0, BSrc s1,
-               float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense,
-               OptK opt) {
-    constexpr int D = LPR * 4;
-    constexpr int GPC = kBT / LPR;
-    __shared__ uint64_t s[kCap];
-    __shared__ unsigned short heads[kCap];
-    __shared__ unsigned short longs[64];
-    __shared__ float4 part[GPC][LPR];
-    __shared__ int wsum[kBT / 32];
-    __shared__ int sh_nu, sh_nlong, sh_next;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int sub = tid % LPR, grp = tid / LPR;
+// first index in the sorted run a[0..n) whose value is >= v (ties cannot occur: (row, position) pairs are unique)
+__device__ __forceinline__ int lower_bound64(const uint64_t* a, int n, uint64_t v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
 
+// ---------------------------------------------------------------------------------------------------
+// k_bucket_sort: one CTA per bucket sorts its (row, position) pairs in place.  Buckets cover ascending, disjoint
+// row ranges, so afterwards the whole pairs array is sorted by (row, position) -- the same order a device-wide
+// radix sort would give, at a fraction of its cost.  Rows with >= kLong contributions are listed for the
+// cooperative kernel.  Buckets larger than the shared-memory capacity (hot rows, tiny tables) are sorted in
+// kCap-sized chunks and then merged pairwise through the `tmp` array.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBT)
+k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const int* __restrict__ off, int nb,
+              int* __restrict__ n_long, uint2* __restrict__ longs, int long_cap) {
+    __shared__ uint64_t s[kCap];
+    const int tid = threadIdx.x;
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
         const int beg = off[b];
         const int cnt = off[b + 1] - beg;
-        if (cnt == 0 || cnt > kCap) continue;      // oversize buckets: k_bucket_apply_big
-        {
-            // ---- load + sort ------------------------------------------------------------------
+        if (cnt == 0) continue;
+        uint64_t* g = pairs + beg;
+        if (cnt <= kCap) {
             int P = 32;
             while (P < cnt) P <<= 1;
-            for (int i = tid; i < P; i += kBT) s[i] = i < cnt ? pairs[beg + i] : ~0ull;
-            if (tid == 0) sh_nlong = 0;
+            for (int i = tid; i < P; i += kBT) s[i] = i < cnt ? g[i] : ~0ull;
             __syncthreads();
             bitonic_sort_smem(s, P);
-            // ---- run heads -> heads[0..nu) ----------------------------------------------------
-            const int E = (P + kBT - 1) / kBT;                 // consecutive elements per thread
-            const int i0 = tid * E;
-            int local = 0;
-            for (int e = 0; e < E; ++e) {
-                const int i = i0 + e;
-                if (i < cnt && (i == 0 || (uint32_t)(s[i] >> 32) != (uint32_t)(s[i - 1] >> 32))) ++local;
-            }
-            int x = local;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(B2R_FULL_MASK, x, o);
-                if (lane >= o) x += y;
-            }
-            if (lane == 31) wsum[warp] = x;
-            __syncthreads();
-            int wbase = 0;
-            for (int wi = 0; wi < warp; ++wi) wbase += wsum[wi];
-            int dst = wbase + x - local;
-            for (int e = 0; e < E; ++e) {
-                const int i = i0 + e;
-                if (i < cnt && (i == 0 || (uint32_t)(s[i] >> 32) != (uint32_t)(s[i - 1] >> 32))) heads[dst++] = (unsigned short)i;
-            }
-            if (tid == kBT - 1) sh_nu = wbase + x;
-            __syncthreads();
-            const int nu = sh_nu;
-            // ---- short rows: kRB consecutive unique rows per lane group, all their loads in flight together ----
-            for (int u0 = grp * kRB; u0 < nu; u0 += GPC * kRB) {
-                int j0[kRB], j1[kRB];
-                int64_t row[kRB];
-                float4 w[kRB], m[kRB], v[kRB], acc[kRB];
-                int maxlen = 0;
-#pragma unroll
-                for (int k = 0; k < kRB; ++k) {
-                    const int u = u0 + k;
-                    j0[k] = j1[k] = 0;
-                    row[k] = -1;
-                    if (u < nu) {
-                        j0[k] = heads[u];
-                        j1[k] = (u + 1 < nu) ? heads[u + 1] : cnt;
-                        if (j1[k] - j0[k] >= kLong) {           // deferred to the cooperative path
-                            if (sub == 0) {
-                                const int q = atomicAdd(&sh_nlong, 1);
-                                if (q < 64) longs[q] = (unsigned short)u;
-                            }
-                            j1[k] = j0[k];
-                        } else {
-                            row[k] = (int64_t)(s[j0[k]] >> 32);
-                            maxlen = max(maxlen, j1[k] - j0[k]);
-                        }
-                    }
-                    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row[k] >= 0) {
-                        if (MODE == 2) {
-                            w[k] = ld4(W + row[k] * D + sub * 4);
-                            if (opt.kind == 1) m[k] = ld4(M + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                            if (opt.kind != 0) v[k] = ld4(V + row[k] * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                        } else {
-                            w[k] = ld4(dense + row[k] * D + sub * 4);
-                        }
+            for (int i = tid; i < cnt; i += kBT) {
+                const uint64_t v = s[i];
+                g[i] = v;
+                const uint32_t key = (uint32_t)(v >> 32);
+                if (i == 0 || (uint32_t)(s[i - 1] >> 32) != key) {          // run head: length by binary search
+                    const int ub = lower_bound64(s, cnt, ((uint64_t)key + 1) << 32);
+                    if (ub - i >= kLong) {
+                        const int q = atomicAdd(n_long, 1);
+                        if (q < long_cap) longs[q] = make_uint2((uint32_t)(beg + i), (uint32_t)(ub - i));
                     }
                 }
-                for (int t = 0; t < maxlen; ++t) {
-#pragma unroll
-                    for (int k = 0; k < kRB; ++k) {
-                        if (j0[k] + t < j1[k]) {
-                            const float* base;
-                            int ld;
-                            int64_t r;
-                            float c;
-                            b_contribution(s0, s1, (uint32_t)s[j0[k] + t], base, ld, r, c);
-                            fma4(acc[k], c, ld4(base + r * ld + sub * 4));
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < kRB; ++k)
-                    if (row[k] >= 0) RowIO<LPR>::template finish<MODE>(row[k], acc[k], sub, w[k], m[k], v[k], W, M, V, dense, opt);
             }
             __syncthreads();
-            // ---- long rows: the whole CTA reduces one row at a time ----------------------------
-            const int nlong = min(sh_nlong, 64);
-            if (nlong > 0) {
-                // deterministic order of the long rows regardless of which group found them first
-                if (tid == 0) {
-                    for (int a = 1; a < nlong; ++a) {
-                        const unsigned short key = longs[a];
-                        int c2 = a - 1;
-                        while (c2 >= 0 && longs[c2] > key) { longs[c2 + 1] = longs[c2]; --c2; }
-                        longs[c2 + 1] = key;
-                    }
+        } else {
+            // chunked shared-memory sorts ...
+            for (int c0 = 0; c0 < cnt; c0 += kCap) {
+                const int m = min(kCap, cnt - c0);
+                int P = 32;
+                while (P < m) P <<= 1;
+                for (int i = tid; i < P; i += kBT) s[i] = i < m ? g[c0 + i] : ~0ull;
+                __syncthreads();
+                bitonic_sort_smem(s, P);
+                for (int i = tid; i < m; i += kBT) g[c0 + i] = s[i];
+                __syncthreads();
+            }
+            // ... then pairwise merges by rank (each element: own index + rank in the sibling run), ping-pong g <-> t
+            uint64_t* src = g;
+            uint64_t* dst = tmp + beg;
+            for (int width = kCap; width < cnt; width <<= 1) {
+                for (int i = tid; i < cnt; i += kBT) {
+                    const int run = i / width;
+                    const int base = (run & ~1) * width;
+                    const int a0 = base, a1 = min(cnt, base + width), b1 = min(cnt, base + 2 * width);
+                    const uint64_t v = src[i];
+                    int pos;
+                    if ((run & 1) == 0) pos = (i - a0) + lower_bound64(src + a1, b1 - a1, v);
+                    else pos = (i - a1) + lower_bound64(src + a0, a1 - a0, v);
+                    dst[base + pos] = v;
                 }
                 __syncthreads();
-                for (int q = 0; q < nlong; ++q) {
-                    const int u = longs[q];
-                    const int j0 = heads[u];
-                    const int j1 = (u + 1 < nu) ? heads[u + 1] : cnt;
-                    const int64_t row = (int64_t)(s[j0] >> 32);
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int j = j0 + grp; j < j1; j += GPC) {
-                        const float* base;
-                        int ld;
-                        int64_t r;
-                        float c;
-                        b_contribution(s0, s1, (uint32_t)s[j], base, ld, r, c);
-                        fma4(acc, c, ld4(base + r * ld + sub * 4));
-                    }
-                    part[grp][sub] = acc;
-                    __syncthreads();
-                    if (grp == 0) {
-                        float4 tot = part[0][sub];
-                        for (int g2 = 1; g2 < GPC; ++g2) {
-                            const float4 y = part[g2][sub];
-                            tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
-                        }
-                        float4 w, m, v;
-                        if (MODE == 2) {
-                            w = ld4(W + row * D + sub * 4);
-                            if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                            if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                        } else {
-                            w = ld4(dense + row * D + sub * 4);
-                        }
-                        RowIO<LPR>::template finish<MODE>(row, tot, sub, w, m, v, W, M, V, dense, opt);
-                    }
-                    __syncthreads();
-                }
-                // more than 64 long rows in one bucket: the rest (never recorded) are handled below by rescanning
-                if (sh_nlong > 64) {
-                    for (int u = 0; u < nu; ++u) {
-                        const int j0 = heads[u];
-                        const int j1 = (u + 1 < nu) ? heads[u + 1] : cnt;
-                        if (j1 - j0 < kLong) continue;
-                        bool seen = false;
-                        for (int q = 0; q < 64; ++q) seen |= (longs[q] == u);
-                        if (seen) continue;
-                        const int64_t row = (int64_t)(s[j0] >> 32);
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        for (int j = j0 + grp; j < j1; j += GPC) {
-                            const float* base;
-                            int ld;
-                            int64_t r;
-                            float c;
-                            b_contribution(s0, s1, (uint32_t)s[j], base, ld, r, c);
-                            fma4(acc, c, ld4(base + r * ld + sub * 4));
-                        }
-                        part[grp][sub] = acc;
-                        __syncthreads();
-                        if (grp == 0) {
-                            float4 tot = part[0][sub];
-                            for (int g2 = 1; g2 < GPC; ++g2) {
-                                const float4 y = part[g2][sub];
-                                tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
-                            }
-                            float4 w, m, v;
-                            if (MODE == 2) {
-                                w = ld4(W + row * D + sub * 4);
-                                if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                                if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                            } else {
-                                w = ld4(dense + row * D + sub * 4);
-                            }
-                            RowIO<LPR>::template finish<MODE>(row, tot, sub, w, m, v, W, M, V, dense, opt);
-                        }
-                        __syncthreads();
+                uint64_t* t2 = src; src = dst; dst = t2;
+            }
+            if (src != g) {
+                for (int i = tid; i < cnt; i += kBT) g[i] = src[i];
+                __syncthreads();
+            }
+            for (int i = tid; i < cnt; i += kBT) {
+                const uint32_t key = (uint32_t)(g[i] >> 32);
+                if (i == 0 || (uint32_t)(g[i - 1] >> 32) != key) {
+                    const int ub = lower_bound64(g, cnt, ((uint64_t)key + 1) << 32);
+                    if (ub - i >= kLong) {
+                        const int q = atomicAdd(n_long, 1);
+                        if (q < long_cap) longs[q] = make_uint2((uint32_t)(beg + i), (uint32_t)(ub - i));
                     }
                 }
             }
@@ -378,122 +284,100 @@ k_bucket_apply(const uint64_t* __restrict__ pairs, const int* __restrict__ off, 
     }
 }
 
-// buckets that do not fit the shared-memory sort (cnt > kCap): rare (hot rows / tiny tables); kept out of the
-// main kernel so that one stays lean in registers
+// ---------------------------------------------------------------------------------------------------
+// k_apply_sorted: one lane group per pair index; the group whose pair is the first of its row owns the row: it
+// requests the weight/state rows, walks the row's contributions (ascending position), applies the update.
+// Rows with >= kLong contributions are left to k_apply_long.  No shared memory, no barriers.
+// ---------------------------------------------------------------------------------------------------
 template <int LPR, int MODE>
 __global__ void __launch_bounds__(kBT)
-k_bucket_apply_big(const uint64_t* __restrict__ pairs, const int* __restrict__ off, int nb, BSrc s0, BSrc s1,
-                   float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense,
-                   OptK opt) {
+k_apply_sorted(const uint64_t* __restrict__ pairs, const int* __restrict__ n_valid_ptr, BSrc s0, BSrc s1,
+               float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense, OptK opt) {
     constexpr int D = LPR * 4;
     constexpr int GPC = kBT / LPR;
-    __shared__ uint64_t s[kCap];
-    __shared__ float4 part[GPC][LPR];
-    __shared__ int wsum[kBT / 32];
-    __shared__ int sh_next;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int sub = tid % LPR, grp = tid / LPR;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        const int beg = off[b];
-        const int cnt = off[b + 1] - beg;
-        if (cnt <= kCap) continue;
-        {
-            // ---- oversize bucket: row by row (ascending), each row in ascending position ranges that fit ----
-            uint32_t last_key = 0;
-            bool first_round = true;
-            for (;;) {
-                // next row id: smallest key > last_key (or any key in the first round)
-                uint32_t kmin = 0xffffffffu;
-                for (int i = tid; i < cnt; i += kBT) {
-                    const uint32_t k = (uint32_t)(pairs[beg + i] >> 32);
-                    if ((first_round || k > last_key) && k < kmin) kmin = k;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(B2R_FULL_MASK, kmin, o));
-                if (lane == 0) wsum[warp] = (int)kmin;
-                __syncthreads();
-                uint32_t key = 0xffffffffu;
-                for (int wi = 0; wi < kBT / 32; ++wi) key = min(key, (uint32_t)wsum[wi]);
-                __syncthreads();
-                if (key == 0xffffffffu) break;
-                first_round = false;
-                last_key = key;
-                const int64_t row = (int64_t)key;
-                float4 total = make_float4(0.f, 0.f, 0.f, 0.f);      // carried by group 0 across ranges
-                uint32_t lo = 0;                                      // positions >= lo still to do
-                bool more = true;
-                while (more) {
-                    // find a range [lo, hi) of positions holding at most kCap occurrences of this key
-                    uint64_t span = 0x100000000ull - lo;
-                    for (;;) {
-                        if (tid == 0) sh_next = 0;
-                        __syncthreads();
-                        const uint64_t hi = (uint64_t)lo + span;
-                        int c = 0;
-                        for (int i = tid; i < cnt; i += kBT) {
-                            const uint64_t pr = pairs[beg + i];
-                            const uint32_t p = (uint32_t)pr;
-                            if ((uint32_t)(pr >> 32) == key && p >= lo && (uint64_t)p < hi) ++c;
-                        }
-                        if (c) atomicAdd(&sh_next, c);
-                        __syncthreads();
-                        const int tot_c = sh_next;
-                        __syncthreads();
-                        if (tot_c <= kCap) break;
-                        span = (span + 1) >> 1;
-                    }
-                    const uint64_t hi = (uint64_t)lo + span;
-                    // gather the range's positions, sort them, reduce cooperatively in fixed order
-                    if (tid == 0) sh_next = 0;
-                    __syncthreads();
-                    for (int i = tid; i < cnt; i += kBT) {
-                        const uint64_t pr = pairs[beg + i];
-                        const uint32_t p = (uint32_t)pr;
-                        if ((uint32_t)(pr >> 32) == key && p >= lo && (uint64_t)p < hi) s[atomicAdd(&sh_next, 1)] = pr;
-                    }
-                    __syncthreads();
-                    const int m_here = sh_next;
-                    int P = 32;
-                    while (P < m_here) P <<= 1;
-                    for (int i = m_here + tid; i < P; i += kBT) s[i] = ~0ull;
-                    __syncthreads();
-                    bitonic_sort_smem(s, P);
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int j = grp; j < m_here; j += GPC) {
-                        const float* base;
-                        int ld;
-                        int64_t r;
-                        float c;
-                        b_contribution(s0, s1, (uint32_t)s[j], base, ld, r, c);
-                        fma4(acc, c, ld4(base + r * ld + sub * 4));
-                    }
-                    part[grp][sub] = acc;
-                    __syncthreads();
-                    if (grp == 0) {
-                        for (int g2 = 0; g2 < GPC; ++g2) {
-                            const float4 y = part[g2][sub];
-                            total.x += y.x; total.y += y.y; total.z += y.z; total.w += y.w;
-                        }
-                    }
-                    __syncthreads();
-                    more = hi < 0x100000000ull;
-                    lo = (uint32_t)hi;
-                }
-                if (grp == 0) {
-                    float4 w, m, v;
-                    if (MODE == 2) {
-                        w = ld4(W + row * D + sub * 4);
-                        if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                        if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                    } else {
-                        w = ld4(dense + row * D + sub * 4);
-                    }
-                    RowIO<LPR>::template finish<MODE>(row, total, sub, w, m, v, W, M, V, dense, opt);
-                }
-                __syncthreads();
+    const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+    const int n_valid = *n_valid_ptr;
+    for (int j = blockIdx.x * GPC + grp; j < n_valid; j += gridDim.x * GPC) {
+        uint64_t cur = pairs[j];
+        const uint32_t key = (uint32_t)(cur >> 32);
+        if (j > 0 && (uint32_t)(pairs[j - 1] >> 32) == key) continue;       // not the head of its row
+        const int64_t row = (int64_t)key;
+        float4 w, m, v;
+        if (MODE == 2) {
+            w = ld4(W + row * D + sub * 4);
+            if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+            if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+        } else {
+            w = ld4(dense + row * D + sub * 4);
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int len = 0;
+        bool is_long = false;
+        for (int jj = j;;) {
+            const float* base;
+            int ld;
+            int64_t r;
+            float c;
+            b_contribution(s0, s1, (uint32_t)cur, base, ld, r, c);
+            fma4(acc, c, ld4(base + r * ld + sub * 4));
+            ++len;
+            if (++jj >= n_valid) break;
+            cur = pairs[jj];
+            if ((uint32_t)(cur >> 32) != key) break;
+            if (len >= kLong) {
+                is_long = true;
+                break;
             }
         }
+        if (is_long) continue;
+        RowIO<LPR>::template finish<MODE>(row, acc, sub, w, m, v, W, M, V, dense, opt);
+    }
+}
+
+// rows with many contributions: the whole CTA reduces one row (contribution t -> group t % GPC, partials combined
+// in group order -> deterministic)
+template <int LPR, int MODE>
+__global__ void __launch_bounds__(kBT)
+k_apply_long(const uint64_t* __restrict__ pairs, const int* __restrict__ n_long_ptr, const uint2* __restrict__ longs,
+             int long_cap, BSrc s0, BSrc s1, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V,
+             float* __restrict__ dense, OptK opt) {
+    constexpr int D = LPR * 4;
+    constexpr int GPC = kBT / LPR;
+    __shared__ float4 part[GPC][LPR];
+    const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+    const int n_long = min(*n_long_ptr, long_cap);
+    for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
+        const uint2 e = longs[q];
+        const int j0 = (int)e.x, len = (int)e.y;
+        const int64_t row = (int64_t)(pairs[j0] >> 32);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = grp; t < len; t += GPC) {
+            const float* base;
+            int ld;
+            int64_t r;
+            float c;
+            b_contribution(s0, s1, (uint32_t)pairs[j0 + t], base, ld, r, c);
+            fma4(acc, c, ld4(base + r * ld + sub * 4));
+        }
+        part[grp][sub] = acc;
+        __syncthreads();
+        if (grp == 0) {
+            float4 tot = part[0][sub];
+            for (int g2 = 1; g2 < GPC; ++g2) {
+                const float4 y = part[g2][sub];
+                tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
+            }
+            float4 w, m, v;
+            if (MODE == 2) {
+                w = ld4(W + row * D + sub * 4);
+                if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+                if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+            } else {
+                w = ld4(dense + row * D + sub * 4);
+            }
+            RowIO<LPR>::template finish<MODE>(row, tot, sub, w, m, v, W, M, V, dense, opt);
+        }
+        __syncthreads();
     }
 }
 
@@ -516,7 +400,8 @@ static BucketGeom bucket_geom(int64_t n, int64_t n_rows) {
 }
 
 struct BucketLayout {
-    size_t count, cursor, off, pairs, total;
+    size_t count, cursor, off, pairs, tmp, longs, total;
+    int long_cap;
 };
 
 static BucketLayout bucket_layout(int64_t n, int64_t n_rows) {
@@ -530,8 +415,11 @@ static BucketLayout bucket_layout(int64_t n, int64_t n_rows) {
     };
     L.count = take((size_t)g.nb * 4 * kPad);
     L.cursor = take((size_t)g.nb * 4 * kPad);
-    L.off = take((size_t)(g.nb + 1) * 4);
+    L.off = take((size_t)(g.nb + 3) * 4);
     L.pairs = take((size_t)n * 8);
+    L.tmp = take((size_t)n * 8);
+    L.long_cap = (int)(n / kLong + 1);
+    L.longs = take((size_t)L.long_cap * 8);
     L.total = o;
     return L;
 }
@@ -595,6 +483,11 @@ extern "C" int b2r_bucket_partition(const int64_t* ids, int64_t n, int64_t n_row
     B2R_LAUNCH_OK("k_bucket_scan");
     k_bucket_scatter<<<grid, kBT, 0, s>>>(ids, n, n_rows, g.shift, ignore_id, ignore_n, cursor, pairs);
     B2R_LAUNCH_OK("k_bucket_scatter");
+    const int sort_cap = sm_count() * 8;
+    k_bucket_sort<<<g.nb < sort_cap ? g.nb : sort_cap, kBT, 0, s>>>(pairs, reinterpret_cast<uint64_t*>(base + L.tmp), off,
+                                                                   g.nb, off + g.nb + 2,
+                                                                   reinterpret_cast<uint2*>(base + L.longs), L.long_cap);
+    B2R_LAUNCH_OK("k_bucket_sort");
     return 0;
 }
 
@@ -624,22 +517,17 @@ extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d
     const int* off = reinterpret_cast<const int*>(base + L.off);
     const uint64_t* pairs = reinterpret_cast<const uint64_t*>(base + L.pairs);
     const BSrc a = to_bsrc(s0, d), b = to_bsrc(s1, d);
-    const int cap = sm_count() * 8;
-    const int grid = g.nb < cap ? g.nb : cap;
-    const int big_grid = g.nb < sm_count() ? g.nb : sm_count();
     const OptK ok = make_optk(o);
-    static int rb = -1;                    // tuning knob B2R_BUCKET_RB = 1 | 2 | 4 (read once)
-    if (rb < 0) {
-        const char* e = getenv("B2R_BUCKET_RB");
-        rb = e ? atoi(e) : 2;
-        if (rb != 1 && rb != 2 && rb != 4) rb = 2;
-    }
+    const uint2* longs = reinterpret_cast<const uint2*>(base + L.longs);
+    const int* n_valid = off + g.nb;                 // total number of (non-ignored) pairs, written by the scan
+    const int* n_long = off + g.nb + 2;
 #define B2R_BK(LPR, MODE)                                                                              \
     do {                                                                                               \
-        if (rb == 1) k_bucket_apply<LPR, MODE, 1><<<grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, ok); \
-        else if (rb == 2) k_bucket_apply<LPR, MODE, 2><<<grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, ok); \
-        else k_bucket_apply<LPR, MODE, 4><<<grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, ok); \
-        k_bucket_apply_big<LPR, MODE><<<big_grid, kBT, 0, s>>>(pairs, off, g.nb, a, b, W, m, v, dense, ok); \
+        constexpr int GPC = kBT / LPR;                                                                 \
+        int64_t need = (n + GPC - 1) / GPC;                                                            \
+        const int64_t cap = (int64_t)sm_count() * 16;                                                  \
+        k_apply_sorted<LPR, MODE><<<(int)(need < cap ? need : cap), kBT, 0, s>>>(pairs, n_valid, a, b, W, m, v, dense, ok); \
+        k_apply_long<LPR, MODE><<<sm_count(), kBT, 0, s>>>(pairs, n_long, longs, L.long_cap, a, b, W, m, v, dense, ok); \
     } while (0)
     if (mode == 1) {
         if (d == 32) B2R_BK(8, 1); else if (d == 64) B2R_BK(16, 1); else B2R_BK(32, 1);
@@ -647,6 +535,6 @@ extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d
         if (d == 32) B2R_BK(8, 2); else if (d == 64) B2R_BK(16, 2); else B2R_BK(32, 2);
     }
 #undef B2R_BK
-    B2R_LAUNCH_OK("k_bucket_apply");
+    B2R_LAUNCH_OK("k_apply_sorted");
     return 0;
 }
