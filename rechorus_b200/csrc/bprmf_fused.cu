@@ -34,62 +34,93 @@ __device__ __forceinline__ float group_max(float v) {
 //   C: g for the own candidate (stored), broadcast inside the group, acc = sum g*row -> shared memory  |barrier|
 //   D: 4*LPR threads per sample add the GPS partials in group order -> dQ (deterministic)
 // Shared buffers alternate by pass parity, so no barrier is needed between passes.
+// sum each of the RPG per-lane values over the LPR lanes of a group with RPG + log2(LPR/RPG) shuffles instead of
+// RPG * log2(LPR): at every step the lanes split the live values in two halves and exchange the half they give up.
+// Afterwards lane `sub` holds the total of value sub / (LPR/RPG)  (lanes of one block of LPR/RPG hold copies).
+template <int LPR, int RPG>
+__device__ __forceinline__ float group_sum_multi(float (&v)[RPG], int sub) {
+    int n = RPG;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        if (n > 1) {
+            const bool upper = (sub & o) != 0;
+            n >>= 1;
+#pragma unroll
+            for (int i = 0; i < RPG / 2; ++i) {
+                if (i < n) {
+                    const float send = upper ? v[i] : v[i + n];
+                    const float keep = upper ? v[i + n] : v[i];
+                    v[i] = keep + __shfl_xor_sync(B2R_FULL_MASK, send, o);
+                }
+            }
+        } else {
+            v[0] += __shfl_xor_sync(B2R_FULL_MASK, v[0], o);
+        }
+    }
+    return v[0];
+}
+
 template <int LPR, int RPG>
 struct FusedPass {
     static constexpr int D = LPR * 4;
     static constexpr int GPC = 256 / LPR;
+    static constexpr int RS = LPR / RPG;                  // lanes per "speaker" block after group_sum_multi
 
     const float* U; const int64_t* uid; int64_t n_users;
     const float* T; const int64_t* ids; int64_t n_t;
     float* pred; float* gout; float* row_loss; float* dQ;
     int B, C, GPS; int32_t* err_flag;
-    int sub, grp, lane, warp, SPB, j, slot, c_mine;
+    int sub, grp, lane, warp, SPB, j, slot;
+    int c_load;          // candidate whose id this lane loads (row `sub` of the group), valid if sub < RPG
+    int c_mine;          // candidate whose score/gradient this lane speaks for (row sub / RS), if sub % RS == 0
     float invB;
 
-    __device__ __forceinline__ int64_t load_id(int64_t pass) const {
+    __device__ __forceinline__ uint32_t load_id(int64_t pass) const {
         const int64_t b = pass * SPB + slot;
-        int64_t my_id = 0;
-        if (b < B && sub < RPG && c_mine < C) my_id = ids[b * C + c_mine];
-        return my_id;
+        int64_t id = 0;
+        if (b < B && sub < RPG && c_load < C) id = checked_id(ids[b * C + c_load], n_t, err_flag);
+        return (uint32_t)id;
     }
 
-    __device__ __forceinline__ void load_rows(int64_t pass, int64_t my_id_raw, float4 (&r)[RPG], float4& q) const {
+    __device__ __forceinline__ void load_rows(int64_t pass, uint32_t my_id, float4 (&r)[RPG], float4& q) const {
         const int64_t b = pass * SPB + slot;
         const bool have = b < B;
         int64_t qrow = 0;
         if (have) qrow = checked_id(uid[b], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
         q = ld4(U + qrow * D + sub * 4);
-        const int64_t my_id = checked_id(my_id_raw, n_t, err_flag);
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
-            const int64_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
+            const uint32_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
             const bool ok = have && (j + GPS * k) < C;
-            r[k] = ok ? ld_row4(T + id_k * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[k] = ok ? ld_row4(T + (size_t)id_k * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 
-    // sred: [SPB][GPS*?]... per-sample scratch: smx[slot][GPS] maxima, ssum[slot][GPS][3] sums, spos[slot] positive score
+    // combine one value per group of the sample (GPS of them, in shared memory) over the lanes of a group
+    template <bool IS_MAX>
+    __device__ __forceinline__ float across_groups(const float* arr, int stride, float ident) const {
+        float a = ident;
+        for (int t = sub; t < GPS; t += LPR) a = IS_MAX ? fmaxf(a, arr[(slot * GPS + t) * stride]) : a + arr[(slot * GPS + t) * stride];
+        return IS_MAX ? group_max<LPR>(a) : group_sum<LPR>(a);
+    }
+
     __device__ __forceinline__ void compute(int64_t pass, const float4 (&r)[RPG], const float4& q, float* smx,
                                             float* ssum, float* spos, float4 (*part)[LPR]) const {
         const int64_t b = pass * SPB + slot;
         const bool have = b < B;
-        const bool mine_ok = have && sub < RPG && c_mine < C;
-        float x = 0.f;                                    // score of the candidate this lane speaks for
+        const bool mine_ok = have && (sub % RS) == 0 && c_mine < C;
+        float d[RPG];
 #pragma unroll
-        for (int k = 0; k < RPG; ++k) {
-            const float v = group_sum<LPR>(dot4(q, r[k]));
-            if (sub == k) x = v;
-        }
+        for (int k = 0; k < RPG; ++k) d[k] = dot4(q, r[k]);
+        const float x = group_sum_multi<LPR, RPG>(d, sub);          // score of candidate c_mine (copies in RS lanes)
         if (mine_ok && pred != nullptr) pred[b * C + c_mine] = x;
         // ---- A: max over this sample's negatives (candidates c >= 1) -------------------------------------
         const bool is_neg = mine_ok && c_mine > 0;
-        float mx = is_neg ? x : -INFINITY;
-        mx = group_max<LPR>(mx);
-        if (sub == 0) smx[slot * GPS + j] = mx;           // one value per group of the sample
+        float mx = group_max<LPR>(is_neg ? x : -INFINITY);
+        if (sub == 0) smx[slot * GPS + j] = mx;
         if (mine_ok && c_mine == 0) spos[slot] = x;
         __syncthreads();
-        mx = -INFINITY;
-        for (int t = 0; t < GPS; ++t) mx = fmaxf(mx, smx[slot * GPS + t]);
+        mx = across_groups<true>(smx, 1, -INFINITY);
         const float p = spos[slot];
         // ---- B: per-candidate terms, per-sample sums ---------------------------------------------------
         float e = 0.f, sg = 0.f;
@@ -106,12 +137,9 @@ struct FusedPass {
             ssum[(slot * GPS + j) * 3 + 2] = Dp;
         }
         __syncthreads();
-        Z = A = Dp = 0.f;
-        for (int t = 0; t < GPS; ++t) {                   // fixed order
-            Z += ssum[(slot * GPS + t) * 3 + 0];
-            A += ssum[(slot * GPS + t) * 3 + 1];
-            Dp += ssum[(slot * GPS + t) * 3 + 2];
-        }
+        Z = across_groups<false>(ssum + 0, 3, 0.f);
+        A = across_groups<false>(ssum + 1, 3, 0.f);
+        Dp = across_groups<false>(ssum + 2, 3, 0.f);
         const float S = (C > 1) ? A / Z : 0.f;
         const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
         const float dS = inside ? -invB / S : 0.f;
@@ -126,7 +154,7 @@ struct FusedPass {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
-            const float gk = __shfl_sync(B2R_FULL_MASK, gmine, k, LPR);
+            const float gk = __shfl_sync(B2R_FULL_MASK, gmine, k * RS, LPR);
             fma4(acc, gk, r[k]);
         }
         part[grp][sub] = acc;
@@ -164,13 +192,15 @@ k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
     f.pred = pred; f.gout = gout; f.row_loss = row_loss; f.dQ = dQ; f.B = B; f.C = C; f.GPS = GPS; f.err_flag = err_flag;
     f.lane = threadIdx.x & 31; f.warp = threadIdx.x >> 5;
     f.sub = threadIdx.x % LPR; f.grp = threadIdx.x / LPR;
-    f.SPB = P::GPC / GPS; f.j = f.grp % GPS; f.slot = f.grp / GPS; f.c_mine = f.j + GPS * f.sub;
+    f.SPB = P::GPC / GPS; f.j = f.grp % GPS; f.slot = f.grp / GPS;
+    f.c_load = f.j + GPS * f.sub;
+    f.c_mine = f.j + GPS * (f.sub / P::RS);
     f.invB = 1.f / (float)B;
     const int64_t npass = ((int64_t)B + f.SPB - 1) / f.SPB;
     const int64_t G = gridDim.x;
     float4 ra[RPG], rb[RPG], qa, qb;
     int64_t p = blockIdx.x;
-    int64_t id_nxt = 0;
+    uint32_t id_nxt = 0;
     if (p < npass) {
         f.load_rows(p, f.load_id(p), ra, qa);
         if (p + G < npass) id_nxt = f.load_id(p + G);

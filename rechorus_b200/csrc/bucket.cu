@@ -27,8 +27,8 @@ struct BSrc {
     const float* coef;
     const int64_t* src_id;
     int64_t n;
-    int32_t div;
     int32_t ld;
+    FastDiv div;
 };
 
 constexpr int kCap = 2048;        // pairs a CTA sorts in shared memory (16 KB)
@@ -40,10 +40,9 @@ __device__ __forceinline__ void b_contribution(const BSrc& s0, const BSrc& s1, u
                                                int& ld, int64_t& row, float& c) {
     const bool first = (int64_t)p < s0.n;
     const int64_t pp = first ? (int64_t)p : (int64_t)p - s0.n;
-    const int div = first ? s0.div : s1.div;
     const int64_t* sid = first ? s0.src_id : s1.src_id;
     const float* cf = first ? s0.coef : s1.coef;
-    int64_t r = (div == 1) ? pp : (int64_t)((uint32_t)pp / (uint32_t)div);
+    int64_t r = (int64_t)fastdiv((uint32_t)pp, first ? s0.div : s1.div);
     if (sid != nullptr) r = sid[r];
     row = r;
     c = (cf != nullptr) ? cf[pp] : 1.f;
@@ -164,7 +163,7 @@ struct RowIO {
             w.x += acc.x; w.y += acc.y; w.z += acc.z; w.w += acc.w;
             st4(dense + row * D + sub * 4, w);
         } else {
-            optk_update4(opt, w, m, v, acc);
+            optk_update4_fast(opt, w, m, v, acc);
             st4(W + row * D + sub * 4, w);
             if (opt.kind == 1) st4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4, m);
             if (opt.kind != 0) st4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4, v);
@@ -425,13 +424,13 @@ static BucketLayout bucket_layout(int64_t n, int64_t n_rows) {
 }
 
 static BSrc to_bsrc(const b2r_grad_source* s, int d) {
-    BSrc r{nullptr, nullptr, nullptr, 0, 1, d};
+    BSrc r{nullptr, nullptr, nullptr, 0, d, make_fastdiv(1)};
     if (s) {
         r.src = s->src;
         r.coef = s->coef;
         r.src_id = s->src_id;
         r.n = s->n;
-        r.div = s->div < 1 ? 1 : s->div;
+        r.div = make_fastdiv(s->div < 1 ? 1u : (uint32_t)s->div);
         r.ld = s->ld > 0 ? s->ld : d;
     }
     return r;

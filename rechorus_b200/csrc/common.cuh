@@ -141,6 +141,53 @@ __device__ __forceinline__ void optk_elem(const OptK& o, float& w, float& m, flo
     }
 }
 
+// Same update with hardware-approximate sqrt / reciprocal (MUFU.RSQ / MUFU.RCP, <= 2 ulp each) for the row-sparse
+// kernels, which are otherwise instruction-bound on the IEEE sqrt and division sequences: the relative deviation of
+// a step is <= ~5e-7, i.e. ~1e-10 absolute at lr = 1e-3.  b2r_dense_optim (exact-reference mode) keeps optk_elem.
+__device__ __forceinline__ void optk_elem_fast(const OptK& o, float& w, float& m, float& v, float gin) {
+    const float g = fmaf(o.wd, w, gin);
+    if (o.kind == 0) {
+        w = fmaf(-o.lr, g, w);
+    } else if (o.kind == 1) {
+        m = fmaf(o.beta1, m, o.omb1 * g);
+        v = fmaf(o.beta2, v, o.omb2 * g * g);
+        const float sq = v * rsqrtf(fmaxf(v, 1e-38f));                  // sqrt(v), 0 at v = 0
+        w = fmaf(-o.step, __fdividef(m, fmaf(sq, o.isb2, o.eps)), w);
+    } else {
+        v = fmaf(g, g, v);
+        const float sq = v * rsqrtf(fmaxf(v, 1e-38f));
+        w = fmaf(-o.lr, __fdividef(g, sq + o.eps), w);
+    }
+}
+
+__device__ __forceinline__ void optk_update4_fast(const OptK& o, float4& w, float4& m, float4& v, const float4& g) {
+    optk_elem_fast(o, w.x, m.x, v.x, g.x);
+    optk_elem_fast(o, w.y, m.y, v.y, g.y);
+    optk_elem_fast(o, w.z, m.z, v.z, g.z);
+    optk_elem_fast(o, w.w, m.w, v.w, g.w);
+}
+
+// unsigned division by a runtime constant as multiply-high + shift (exact for all 32-bit numerators)
+struct FastDiv {
+    uint32_t mul, sh1, sh2, div;
+};
+
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.div = d < 1 ? 1 : d;
+    uint32_t l = 0;
+    while (l < 32 && ((uint64_t)1 << l) < f.div) ++l;                    // ceil(log2 d)
+    f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - f.div)) / f.div + 1);
+    f.sh1 = l < 1 ? l : 1;
+    f.sh2 = l < 1 ? 0 : l - 1;
+    return f;
+}
+
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) {
+    const uint32_t t = __umulhi(n, f.mul);
+    return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
 __device__ __forceinline__ void optk_update4(const OptK& o, float4& w, float4& m, float4& v, const float4& g) {
     optk_elem(o, w.x, m.x, v.x, g.x);
     optk_elem(o, w.y, m.y, v.y, g.y);
