@@ -60,6 +60,16 @@ __device__ __forceinline__ float group_sum_multi(float (&v)[RPG], int sub) {
     return v[0];
 }
 
+// One pass = SPB = GPC/GPS samples.  Per pass, per lane group (LPR lanes, RPG candidate rows + the positive's row):
+//   dots        the group's RPG scores and, redundantly in every group, the positive's score p (its row is an L1/L2
+//               hit after the first group) -- so no cross-group exchange is needed before the sigmoid;
+//   local stats m_g = max of the group's negatives, e = exp(x - m_g), s = sigmoid(p - x), group sums Z_g, A_g, D_g
+//               -> 4 floats per group to shared memory                                           |barrier 1|
+//   combine     lane t reads group t's 4 floats; M = max m_t, rescale by exp(m_t - M) (online softmax), group sums
+//               -> S, dS, 1/Z; gradient g of the own candidate; acc = sum_k g_k * row_k -> shared |barrier 2|
+//   reduce      4*LPR threads per sample add the GPS partial dQ vectors in group order (deterministic).
+// Shared buffers alternate by pass parity, so no third barrier is needed.  Transcendentals use the fast
+// hardware forms (ex2/rcp based, <= 2 ulp): deviations are ~1e-7 relative on g, far inside the 1e-5 bar.
 template <int LPR, int RPG>
 struct FusedPass {
     static constexpr int D = LPR * 4;
@@ -70,24 +80,23 @@ struct FusedPass {
     const float* T; const int64_t* ids; int64_t n_t;
     float* pred; float* gout; float* row_loss; float* dQ;
     int B, C, GPS; int32_t* err_flag;
-    int sub, grp, lane, warp, SPB, j, slot;
+    int sub, grp, SPB, j, slot;
     int c_load;          // candidate whose id this lane loads (row `sub` of the group), valid if sub < RPG
     int c_mine;          // candidate whose score/gradient this lane speaks for (row sub / RS), if sub % RS == 0
     float invB;
 
-    __device__ __forceinline__ uint32_t load_id(int64_t pass) const {
-        const int64_t b = pass * SPB + slot;
-        int64_t id = 0;
-        if (b < B && sub < RPG && c_load < C) id = checked_id(ids[b * C + c_load], n_t, err_flag);
-        return (uint32_t)id;
-    }
-
-    __device__ __forceinline__ void load_rows(int64_t pass, uint32_t my_id, float4 (&r)[RPG], float4& q) const {
+    __device__ __forceinline__ void load_rows(int64_t pass, float4 (&r)[RPG], float4& rp, float4& q) const {
         const int64_t b = pass * SPB + slot;
         const bool have = b < B;
         int64_t qrow = 0;
-        if (have) qrow = checked_id(uid[b], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
+        uint32_t my_id = 0, pos_id = 0;
+        if (have) {
+            qrow = checked_id(uid[b], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
+            if (sub < RPG && c_load < C) my_id = (uint32_t)checked_id(ids[b * C + c_load], n_t, err_flag);
+            pos_id = (uint32_t)checked_id(ids[b * C], n_t, nullptr);
+        }
         q = ld4(U + qrow * D + sub * 4);
+        rp = have ? ld4(T + (size_t)pos_id * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
             const uint32_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
@@ -96,61 +105,66 @@ struct FusedPass {
         }
     }
 
-    // combine one value per group of the sample (GPS of them, in shared memory) over the lanes of a group
-    template <bool IS_MAX>
-    __device__ __forceinline__ float across_groups(const float* arr, int stride, float ident) const {
-        float a = ident;
-        for (int t = sub; t < GPS; t += LPR) a = IS_MAX ? fmaxf(a, arr[(slot * GPS + t) * stride]) : a + arr[(slot * GPS + t) * stride];
-        return IS_MAX ? group_max<LPR>(a) : group_sum<LPR>(a);
-    }
-
-    __device__ __forceinline__ void compute(int64_t pass, const float4 (&r)[RPG], const float4& q, float* smx,
-                                            float* ssum, float* spos, float4 (*part)[LPR]) const {
+    // STOP (debug bisect knob, B2R_FUSED_STOP): 1 = scores only, 2 = + loss statistics, 3 = everything (default)
+    template <int STOP>
+    __device__ __forceinline__ void compute(int64_t pass, const float4 (&r)[RPG], const float4& rp, const float4& q,
+                                            float4* sstat, float4 (*part)[LPR]) const {
         const int64_t b = pass * SPB + slot;
         const bool have = b < B;
         const bool mine_ok = have && (sub % RS) == 0 && c_mine < C;
         float d[RPG];
 #pragma unroll
         for (int k = 0; k < RPG; ++k) d[k] = dot4(q, r[k]);
-        const float x = group_sum_multi<LPR, RPG>(d, sub);          // score of candidate c_mine (copies in RS lanes)
+        const float p = group_sum<LPR>(dot4(q, rp));                 // positive's score, known to every group
+        const float x = group_sum_multi<LPR, RPG>(d, sub);           // score of candidate c_mine (copies in RS lanes)
         if (mine_ok && pred != nullptr) pred[b * C + c_mine] = x;
-        // ---- A: max over this sample's negatives (candidates c >= 1) -------------------------------------
+        if (STOP == 1) {
+            if (mine_ok) gout[b * C + c_mine] = x;
+            return;
+        }
+        // ---- group-local statistics over this group's negatives ----------------------------------------
         const bool is_neg = mine_ok && c_mine > 0;
-        float mx = group_max<LPR>(is_neg ? x : -INFINITY);
-        if (sub == 0) smx[slot * GPS + j] = mx;
-        if (mine_ok && c_mine == 0) spos[slot] = x;
-        __syncthreads();
-        mx = across_groups<true>(smx, 1, -INFINITY);
-        const float p = spos[slot];
-        // ---- B: per-candidate terms, per-sample sums ---------------------------------------------------
+        const float mg = group_max<LPR>(is_neg ? x : -INFINITY);
         float e = 0.f, sg = 0.f;
         if (is_neg) {
-            e = expf(x - mx);
-            sg = sigmoidf_f(p - x);
+            e = __expf(x - mg);
+            sg = __fdividef(1.f, 1.f + __expf(x - p));
         }
-        float Z = group_sum<LPR>(e);
-        float A = group_sum<LPR>(e * sg);
-        float Dp = group_sum<LPR>(e * sg * (1.f - sg));
-        if (sub == 0) {
-            ssum[(slot * GPS + j) * 3 + 0] = Z;
-            ssum[(slot * GPS + j) * 3 + 1] = A;
-            ssum[(slot * GPS + j) * 3 + 2] = Dp;
-        }
+        const float es = e * sg;
+        const float Zg = group_sum<LPR>(e);
+        const float Ag = group_sum<LPR>(es);
+        const float Dg = group_sum<LPR>(es * (1.f - sg));
+        if (sub == 0) sstat[slot * GPS + j] = make_float4(mg, Zg, Ag, Dg);
         __syncthreads();
-        Z = across_groups<false>(ssum + 0, 3, 0.f);
-        A = across_groups<false>(ssum + 1, 3, 0.f);
-        Dp = across_groups<false>(ssum + 2, 3, 0.f);
-        const float S = (C > 1) ? A / Z : 0.f;
+        // ---- combine the GPS groups of the sample (online-softmax rescale), lanes in parallel --------------
+        float m_t = -INFINITY, Z = 0.f, A = 0.f, Dp = 0.f;
+        for (int t = sub; t < GPS; t += LPR) {                       // one iteration unless GPS > LPR
+            const float4 st = sstat[slot * GPS + t];
+            if (st.x > m_t) {                                        // rescale what was accumulated so far
+                const float sc = __expf(m_t - st.x);
+                Z *= sc; A *= sc; Dp *= sc;
+                m_t = st.x;
+            }
+            const float sc2 = (st.x == -INFINITY) ? 0.f : __expf(st.x - m_t);
+            Z = fmaf(st.y, sc2, Z); A = fmaf(st.z, sc2, A); Dp = fmaf(st.w, sc2, Dp);
+        }
+        const float M = group_max<LPR>(m_t);
+        const float scl = (m_t == -INFINITY) ? 0.f : __expf(m_t - M);
+        Z = group_sum<LPR>(Z * scl);
+        A = group_sum<LPR>(A * scl);
+        Dp = group_sum<LPR>(Dp * scl);
+        const float S = (C > 1) ? __fdividef(A, Z) : 0.f;
         const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
-        const float dS = inside ? -invB / S : 0.f;
-        const float invZ = (C > 1) ? 1.f / Z : 0.f;
-        // ---- C: gradient of the own candidate, acc = sum_k g_k * row_k ----------------------------------
+        const float dS = inside ? -__fdividef(invB, S) : 0.f;
+        const float invZ = (C > 1) ? __fdividef(1.f, Z) : 0.f;
         float gmine = 0.f;
         if (mine_ok) {
-            gmine = (c_mine == 0) ? dS * Dp * invZ : dS * (e * invZ) * ((sg - S) - sg * (1.f - sg));
+            const float ef = is_neg ? e * __expf(mg - M) : 0.f;      // e relative to the sample max
+            gmine = (c_mine == 0) ? dS * Dp * invZ : dS * (ef * invZ) * ((sg - S) - sg * (1.f - sg));
             gout[b * C + c_mine] = gmine;
         }
         if (have && j == 0 && sub == 0) row_loss[b] = -logf(fminf(fmaxf(S, 1e-8f), 1.f - 1e-8f));
+        if (STOP == 2) return;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
@@ -159,7 +173,6 @@ struct FusedPass {
         }
         part[grp][sub] = acc;
         __syncthreads();
-        // ---- D: ordered combine: thread (slot, column) sums the GPS partials of its sample ----------------
         {
             const float* pf = reinterpret_cast<const float*>(part);
             for (int o = threadIdx.x; o < SPB * D; o += 256) {
@@ -175,49 +188,54 @@ struct FusedPass {
     }
 };
 
-template <int LPR, int RPG>
-__global__ void __launch_bounds__(256, 2)
+template <int LPR, int RPG, int STOP>
+__global__ void __launch_bounds__(256, (RPG <= 4) ? 4 : 3)
 k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int64_t n_users,
               const float* __restrict__ T, const int64_t* __restrict__ ids, int64_t n_t,
               float* __restrict__ pred, float* __restrict__ gout, float* __restrict__ row_loss,
-              float* __restrict__ dQ, int B, int C, int GPS, int32_t* err_flag) {
+              float* __restrict__ dQ, int B, int C, int GPS, int32_t* err_flag, float* __restrict__ loss_out,
+              unsigned int* __restrict__ done_counter) {
     static_assert(RPG <= LPR, "ids of a group's rows are loaded one per lane");
     using P = FusedPass<LPR, RPG>;
-    __shared__ float smx[2][P::GPC];
-    __shared__ float ssum[2][P::GPC * 3];
-    __shared__ float spos[2][P::GPC];
-    __shared__ float4 part[2][P::GPC][LPR];               // partial dQ per group (alternating by pass parity)
+    __shared__ float4 sstat[2][P::GPC];                   // (max, Z, A, D) per group, alternating by pass parity
+    __shared__ float4 part[2][P::GPC][LPR];               // partial dQ per group
     P f;
     f.U = U; f.uid = uid; f.n_users = n_users; f.T = T; f.ids = ids; f.n_t = n_t;
     f.pred = pred; f.gout = gout; f.row_loss = row_loss; f.dQ = dQ; f.B = B; f.C = C; f.GPS = GPS; f.err_flag = err_flag;
-    f.lane = threadIdx.x & 31; f.warp = threadIdx.x >> 5;
     f.sub = threadIdx.x % LPR; f.grp = threadIdx.x / LPR;
     f.SPB = P::GPC / GPS; f.j = f.grp % GPS; f.slot = f.grp / GPS;
     f.c_load = f.j + GPS * f.sub;
     f.c_mine = f.j + GPS * (f.sub / P::RS);
     f.invB = 1.f / (float)B;
     const int64_t npass = ((int64_t)B + f.SPB - 1) / f.SPB;
-    const int64_t G = gridDim.x;
-    float4 ra[RPG], rb[RPG], qa, qb;
-    int64_t p = blockIdx.x;
-    uint32_t id_nxt = 0;
-    if (p < npass) {
-        f.load_rows(p, f.load_id(p), ra, qa);
-        if (p + G < npass) id_nxt = f.load_id(p + G);
+    int par = 0;
+    for (int64_t p = blockIdx.x; p < npass; p += gridDim.x, par ^= 1) {
+        float4 r[RPG], rp, q;
+        f.load_rows(p, r, rp, q);
+        f.template compute<STOP>(p, r, rp, q, sstat[par], part[par]);
     }
-    for (; p < npass; p += 2 * G) {
-        const int64_t p1 = p + G, p2 = p + 2 * G, p3 = p + 3 * G;
-        if (p1 < npass) {
-            f.load_rows(p1, id_nxt, rb, qb);              // rows of the next pass in flight during this one
-            if (p2 < npass) id_nxt = f.load_id(p2);        // ids of the pass after that
-        }
-        f.compute(p, ra, qa, smx[0], ssum[0], spos[0], part[0]);
-        if (p1 < npass) {
-            if (p2 < npass) {
-                f.load_rows(p2, id_nxt, ra, qa);
-                if (p3 < npass) id_nxt = f.load_id(p3);
+    // mean of the per-sample losses by the last CTA to finish (fixed summation order -> deterministic)
+    if (loss_out != nullptr) {
+        __shared__ bool last;
+        __shared__ float red[256];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            float a = 0.f;
+            for (int i = threadIdx.x; i < B; i += 256) a += __ldcg(row_loss + i);
+            red[threadIdx.x] = a;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+                __syncthreads();
             }
-            f.compute(p1, rb, qb, smx[1], ssum[1], spos[1], part[1]);
+            if (threadIdx.x == 0) {
+                loss_out[0] = red[0] / (float)B;
+                *done_counter = 0u;                      // ready for the next launch
+            }
         }
     }
 }
@@ -251,10 +269,30 @@ static bool pick_shape(int C, int GPC, int max_rpg, int* RPG, int* GPS) {
 using namespace b2r;
 
 // returns B2R_E_UNSUPPORTED (without touching the error string semantics) when the shape has no fused variant
+static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
+                        int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, int B, int C, int d,
+                        int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream);
+
 extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64_t n_users, const float* I,
                                        const int64_t* iid, int64_t n_items, float* pred, float* grad_pred,
                                        float* row_loss, float* dQ, int B, int C, int d, int32_t* err_flag,
                                        b2r_stream_t stream) {
+    return fused_launch(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, d, err_flag, nullptr, nullptr,
+                        stream);
+}
+
+// same, and the mean loss is produced by the kernel itself (done_counter: a zero-initialised device word the kernel
+// leaves zero again); used by the step context
+int b2r_bprmf_fused_fwd_bwd_loss(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
+                                 int64_t n_items, float* grad_pred, float* row_loss, float* dQ, int B, int C, int d,
+                                 int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream) {
+    return fused_launch(U, uid, n_users, I, iid, n_items, nullptr, grad_pred, row_loss, dQ, B, C, d, err_flag, loss_out,
+                        done_counter, stream);
+}
+
+static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
+                        int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, int B, int C, int d,
+                        int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream) {
     B2R_REQUIRE(U && uid && I && iid && grad_pred && row_loss && dQ, B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: null pointer");
     B2R_REQUIRE(B > 0 && C > 0, B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: B=%d C=%d", B, C);
     B2R_REQUIRE(aligned16(U) && aligned16(I) && aligned16(dQ), B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: alignment");
@@ -267,9 +305,26 @@ extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64
     const int64_t need = ((int64_t)B + SPB - 1) / SPB;          // passes
     const int64_t cap = (int64_t)sm_count() * 2;                // persistent: 2 resident CTAs per SM, each pipelined
     const int grid = (int)(need < cap ? need : cap);
+    static int stop = -1;
+    if (stop < 0) {
+        const char* e = getenv("B2R_FUSED_STOP");
+        stop = e ? atoi(e) : 3;
+        if (stop < 1 || stop > 3) stop = 3;
+    }
+    static int grid_mul = -1;
+    if (grid_mul < 0) {
+        const char* e = getenv("B2R_FUSED_GRID");
+        grid_mul = e ? atoi(e) : 6;
+        if (grid_mul < 1 || grid_mul > 32) grid_mul = 6;
+    }
+    const int64_t cap2 = (int64_t)sm_count() * grid_mul;
+    const int grid2 = (int)(need < cap2 ? need : cap2);
 #define B2R_FUSED(LPR, R)                                                                              \
-    k_bprmf_fused<LPR, R><<<grid, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, \
-                                               GPS, err_flag)
+    do {                                                                                               \
+        if (stop == 1) k_bprmf_fused<LPR, R, 1><<<grid2, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, GPS, err_flag, loss_out, done_counter); \
+        else if (stop == 2) k_bprmf_fused<LPR, R, 2><<<grid2, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, GPS, err_flag, loss_out, done_counter); \
+        else k_bprmf_fused<LPR, R, 3><<<grid2, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, GPS, err_flag, loss_out, done_counter); \
+    } while (0)
     if (d == 32) {
         if (RPG == 2) B2R_FUSED(8, 2); else if (RPG == 4) B2R_FUSED(8, 4); else B2R_FUSED(8, 8);
     } else if (d == 64) {

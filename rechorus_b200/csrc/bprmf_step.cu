@@ -14,6 +14,10 @@ extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64
                                        float* row_loss, float* dQ, int B, int C, int d, int32_t* err_flag,
                                        b2r_stream_t stream);
 
+int b2r_bprmf_fused_fwd_bwd_loss(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
+                                 int64_t n_items, float* grad_pred, float* row_loss, float* dQ, int B, int C, int d,
+                                 int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream);
+
 namespace b2r {
 
 struct PlanBuf {
@@ -21,7 +25,7 @@ struct PlanBuf {
 };
 
 struct StepLayout {
-    size_t q, pred, g, rows, dQ;
+    size_t q, pred, g, rows, dQ, counter;
     PlanBuf plan[2];
     size_t iws_bytes, uws_bytes;
     size_t total;
@@ -40,6 +44,7 @@ static bool step_layout(int B, int C, int d, int64_t n_users, int64_t n_items, S
     L->g = take(n * 4);
     L->rows = take((size_t)B * 4);
     L->dQ = take((size_t)B * d * 4);
+    L->counter = take(256);
     L->iws_bytes = b2r_bucket_workspace_bytes((int64_t)n, n_items);
     L->uws_bytes = b2r_bucket_workspace_bytes(B, n_users);
     for (int s = 0; s < 2; ++s) {
@@ -98,6 +103,11 @@ extern "C" int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[1], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete c;
+        return set_error((int)e, "b2r_bprmf_ctx_create: %s", cudaGetErrorString(e));
+    }
+    e = cudaMemsetAsync(c->ws + c->L.counter, 0, 256, c->side);
     if (e != cudaSuccess) {
         delete c;
         return set_error((int)e, "b2r_bprmf_ctx_create: %s", cudaGetErrorString(e));
@@ -185,17 +195,14 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
 
     // main: forward + loss + query-side backward
     profile_begin(B2R_PROF_SCORE_FWD, main_s);
-    rc = b2r_bprmf_fused_fwd_bwd(t->U, uid, t->n_users, t->I, iid, t->n_items, nullptr, g, rows, dQ, B, C, d, err_flag,
-                                 main_s);
+    rc = b2r_bprmf_fused_fwd_bwd_loss(t->U, uid, t->n_users, t->I, iid, t->n_items, g, rows, dQ, B, C, d, err_flag, loss_out,
+                                      reinterpret_cast<unsigned int*>(base + c->L.counter), main_s);
     const bool fused = (rc == 0);
     if (rc != 0 && rc != B2R_E_UNSUPPORTED) return rc;
     if (fused) profile_end(B2R_PROF_SCORE_FWD, main_s);
     const float* item_src = t->U;           // dI = g * U[uid[b]]  (U is updated only after the item table)
     const int64_t* item_src_id = uid;
-    if (fused) {
-        rc = launch_mean_rows(rows, loss_out, B, main_s);
-        if (rc != 0) return rc;
-    } else {
+    if (!fused) {
         float* q = reinterpret_cast<float*>(base + c->L.q);
         rc = b2r_gather_rows(t->U, uid, t->n_users, q, B, d, err_flag, main_s);
         if (rc != 0) return rc;

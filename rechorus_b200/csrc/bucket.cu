@@ -12,7 +12,7 @@
 //     k_apply_sorted  one lane group per pair; the group holding the first pair of a row owns the row: requests
 //         w (m, v), walks the row's contributions in ascending position, applies SGD/Adam/Adagrad in place (mode 2)
 //         or adds into a dense gradient (mode 1).  No shared memory, no barriers, no atomics.
-//     k_apply_long    rows with >= kLong contributions, reduced by a whole CTA in a fixed order.
+//         Rows with >= kLong contributions (listed by the sort) are then reduced by whole CTAs in a fixed order.
 // Every sum has a fixed order whatever order the partition's atomics produced -> same bits on every run.
 // Replaces ATen embedding_dense_backward + the dense grad zero-fill + the embedding part of optimizer.step()
 // (helpers/BaseRunner.py:193,205,206).
@@ -290,10 +290,12 @@ k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const in
 // ---------------------------------------------------------------------------------------------------
 template <int LPR, int MODE>
 __global__ void __launch_bounds__(kBT)
-k_apply_sorted(const uint64_t* __restrict__ pairs, const int* __restrict__ n_valid_ptr, BSrc s0, BSrc s1,
+k_apply_sorted(const uint64_t* __restrict__ pairs, const int* __restrict__ n_valid_ptr, const int* __restrict__ n_long_ptr,
+               const uint2* __restrict__ longs, int long_cap, BSrc s0, BSrc s1,
                float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense, OptK opt) {
     constexpr int D = LPR * 4;
     constexpr int GPC = kBT / LPR;
+    __shared__ float4 part[GPC][LPR];          // only touched when the batch has rows with >= kLong contributions
     const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
     const int n_valid = *n_valid_ptr;
     for (int j = blockIdx.x * GPC + grp; j < n_valid; j += gridDim.x * GPC) {
@@ -331,19 +333,8 @@ k_apply_sorted(const uint64_t* __restrict__ pairs, const int* __restrict__ n_val
         if (is_long) continue;
         RowIO<LPR>::template finish<MODE>(row, acc, sub, w, m, v, W, M, V, dense, opt);
     }
-}
-
-// rows with many contributions: the whole CTA reduces one row (contribution t -> group t % GPC, partials combined
-// in group order -> deterministic)
-template <int LPR, int MODE>
-__global__ void __launch_bounds__(kBT)
-k_apply_long(const uint64_t* __restrict__ pairs, const int* __restrict__ n_long_ptr, const uint2* __restrict__ longs,
-             int long_cap, BSrc s0, BSrc s1, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V,
-             float* __restrict__ dense, OptK opt) {
-    constexpr int D = LPR * 4;
-    constexpr int GPC = kBT / LPR;
-    __shared__ float4 part[GPC][LPR];
-    const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+    // rows with many contributions (listed by k_bucket_sort): the whole CTA reduces one row -- contribution t goes to
+    // group t % GPC, partials are combined in group order -> deterministic.  Normally the list is empty.
     const int n_long = min(*n_long_ptr, long_cap);
     for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
         const uint2 e = longs[q];
@@ -525,8 +516,8 @@ extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d
         constexpr int GPC = kBT / LPR;                                                                 \
         int64_t need = (n + GPC - 1) / GPC;                                                            \
         const int64_t cap = (int64_t)sm_count() * 16;                                                  \
-        k_apply_sorted<LPR, MODE><<<(int)(need < cap ? need : cap), kBT, 0, s>>>(pairs, n_valid, a, b, W, m, v, dense, ok); \
-        k_apply_long<LPR, MODE><<<sm_count(), kBT, 0, s>>>(pairs, n_long, longs, L.long_cap, a, b, W, m, v, dense, ok); \
+        k_apply_sorted<LPR, MODE><<<(int)(need < cap ? need : cap), kBT, 0, s>>>(pairs, n_valid, n_long, longs, L.long_cap, \
+                                                                                a, b, W, m, v, dense, ok);       \
     } while (0)
     if (mode == 1) {
         if (d == 32) B2R_BK(8, 1); else if (d == 64) B2R_BK(16, 1); else B2R_BK(32, 1);
