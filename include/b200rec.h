@@ -193,6 +193,11 @@ B2R_API int b2r_dense_optim(float* W, const float* grad, float* m, float* v, int
  * ---------------------------------------------------------------------------------------------- */
 B2R_API int b2r_linear_fwd(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy,
                    int64_t M, int N, int K, int relu, b2r_stream_t stream);
+/* Same forward on the tensor cores: tcgen05.mma kind::tf32 with the accumulator in TMEM and a 4-product hi/lo operand
+ * split (error ~2^-21 relative, i.e. fp32 class).  K % 32 == 0 (<= 128), N % 16 == 0 (<= 256), contiguous W.  Returns
+ * B2R_E_UNSUPPORTED outside that class. */
+B2R_API int b2r_linear_fwd_tc(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy,
+                      int64_t M, int N, int K, int relu, b2r_stream_t stream);
 B2R_API int b2r_linear_bwd_input(const float* dY, int lddy, const float* relu_out, const float* W, float* dX, int lddx,
                          int64_t M, int N, int K, b2r_stream_t stream);
 B2R_API size_t b2r_linear_bwd_weight_workspace_bytes(int64_t M, int N, int K);

@@ -1,0 +1,225 @@
+// linear_tc.cu -- nn.Linear forward on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in TMEM)
+// with fp32-class accuracy: every operand is split x = hi + lo (hi = the TF32 truncation the hardware would apply
+// anyway, lo = the exact remainder) and four products hi*hi + hi*lo + lo*hi + lo*lo are accumulated in the same
+// TMEM tile, which brings the result to ~2^-21 relative of the fp32 answer (the 1e-5 parity bar of the north star
+// rules out a single TF32 product at trained-scale weights).
+//
+// Shape class: the q/k/v and feed-forward Linear layers of utils/layers.py:26-28,106-107 and NeuMF's tower
+// (NeuMF.py:70): Y[M,N] = act(X[M,K] W^T + b) with small K (multiple of 32 floats, <= 128) and N (multiple of 16,
+// <= 256) and M = B*L in the hundreds of thousands -- each CTA owns 128-row tiles of X, W stays resident in shared
+// memory for the CTA's lifetime, so the kernel streams X once and Y once (HBM-bound) while the MMAs ride along.
+//
+// Operand staging: no TMA.  Threads load X / W with coalesced 128-bit loads, split hi/lo in registers and store both
+// halves into shared memory in the canonical K-major SWIZZLE_128B layout the UMMA descriptor expects (one 128-byte
+// row = 32 floats of K; 16-byte chunk index XOR (row & 7); 8-row groups 1024 bytes apart), then
+// fence.proxy.async + barrier, and ONE thread issues the 4*(K/8) MMAs and commits them to an mbarrier.  The epilogue
+// reads the accumulator back with tcgen05.ld (32 lanes x 16 columns per instruction), adds the bias, applies ReLU and
+// writes Y.
+#include "common.cuh"
+
+namespace b2r {
+
+constexpr int TC_M = 128;          // rows per tile == UMMA M
+constexpr int TC_THREADS = 128;    // 4 warps: warp w reads TMEM lanes [32w, 32w+32)
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
+    // K-major, SWIZZLE_128B: start address >> 4 in [0,14); LBO (ignored for swizzled K-major) = 1 in [16,30);
+    // SBO = 1024 B >> 4 = 64 in [32,46); descriptor version 1 (Blackwell) in [46,48); layout type 2 in [61,64)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+
+// bounded wait: a wrong descriptor must end in a trap, not in a hung GPU
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = tc_smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 4 floats into TF32-truncated high parts and exact remainders, store both at the swizzled chunk position
+__device__ __forceinline__ void tc_store_split(char* hi_base, char* lo_base, int row, int chunk, const float4& v) {
+    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) * 16);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi_base + off) = h;
+    *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+// dynamic shared memory (1024-byte aligned): A_hi[KS][128*128B] A_lo[...] B_hi[KS][N*128B] B_lo[...]
+__global__ void __launch_bounds__(TC_THREADS)
+k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                float* __restrict__ Y, int ldy, int M, int N, int K, int relu, int tmem_cols) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_sh;
+    const int KS = K / 32;                                  // 128-byte K slabs
+    const size_t a_slab = (size_t)TC_M * 128, b_slab = (size_t)N * 128;
+    // swizzle-128B operand tiles need 1024-byte aligned bases: align by hand (the launch adds 1 KB of slack)
+    char* A_hi = reinterpret_cast<char*>(smem_raw) + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+    char* A_lo = A_hi + KS * a_slab;
+    char* B_hi = A_lo + KS * a_slab;
+    char* B_lo = B_hi + KS * b_slab;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_sh)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        tc_mbar_init(&mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // W -> B_hi / B_lo (once per CTA): element (n, slab s, chunk c) <- W[n*K + s*32 + c*4 ..]
+    for (int e = tid; e < N * KS * 8; e += TC_THREADS) {
+        const int c = e % 8, s = (e / 8) % KS, n = e / (8 * KS);
+        const float4 v = *reinterpret_cast<const float4*>(W + (size_t)n * K + s * 32 + c * 4);
+        tc_store_split(B_hi + s * b_slab, B_lo + s * b_slab, n, c, v);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_sh;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+    uint32_t parity = 0;
+    const int ntiles = (M + TC_M - 1) / TC_M;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = tile * TC_M;
+        // X tile -> A_hi / A_lo
+        for (int e = tid; e < TC_M * KS * 8; e += TC_THREADS) {
+            const int c = e % 8, s = (e / 8) % KS, r = e / (8 * KS);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < M) v = ld_row4(X + (size_t)(m0 + r) * ldx + s * 32 + c * 4);
+            tc_store_split(A_hi + s * a_slab, A_lo + s * a_slab, r, c, v);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async proxy (UMMA)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int prod = 0; prod < 4; ++prod) {
+                const char* Ab = (prod < 2) ? A_hi : A_lo;              // hi*hi, hi*lo, lo*hi, lo*lo
+                const char* Bb = (prod & 1) ? B_lo : B_hi;
+                for (int s = 0; s < KS; ++s) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {                       // 4 MMAs of K = 8 floats (32 bytes) per slab
+                        const uint64_t ad = tc_desc(tc_smem_u32(Ab + s * a_slab) + k * 32);
+                        const uint64_t bd = tc_desc(tc_smem_u32(Bb + s * b_slab) + k * 32);
+                        tc_mma_tf32(tmem, ad, bd, idesc, acc);
+                        acc = 1;
+                    }
+                }
+            }
+            tc_commit(&mma_bar);
+        }
+        tc_mbar_wait(&mma_bar, parity);
+        parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: thread = row (TMEM lane), 16 columns per tcgen05.ld
+        const int row = m0 + warp * 32 + lane;
+        for (int c0 = 0; c0 < N; c0 += 16) {
+            float v[16];
+            tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            if (row < M) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float y = v[i] + (bias != nullptr ? bias[c0 + i] : 0.f);
+                    if (relu) y = fmaxf(y, 0.f);
+                    v[i] = y;
+                }
+                float* dst = Y + (size_t)row * ldy + c0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                                 // TMEM and the A buffers are free again
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+    }
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+// returns B2R_E_UNSUPPORTED for shapes outside the tensor-core kernel's class (callers fall back to b2r_linear_fwd)
+extern "C" int b2r_linear_fwd_tc(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int64_t M,
+                                 int N, int K, int relu, b2r_stream_t stream) {
+    B2R_REQUIRE(X && W && Y, B2R_E_BADARG, "b2r_linear_fwd_tc: null pointer");
+    if (!(K % 32 == 0 && K >= 32 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 256 && M > 0 && M <= 0x7fffffff &&
+          ldx % 4 == 0 && ldy % 4 == 0 && aligned16(X) && aligned16(W) && aligned16(Y)))
+        return set_error(B2R_E_UNSUPPORTED, "b2r_linear_fwd_tc: shape M=%lld N=%d K=%d ldx=%d ldy=%d outside the kernel's class",
+                         (long long)M, N, K, ldx, ldy);
+    const int KS = K / 32;
+    const size_t smem = (size_t)2 * KS * TC_M * 128 + (size_t)2 * KS * N * 128 + 1024;
+    if (smem > 200 * 1024) return set_error(B2R_E_UNSUPPORTED, "b2r_linear_fwd_tc: %zu B of shared memory needed", smem);
+    int cols = 32;
+    while (cols < N) cols <<= 1;
+    B2R_CUDA_OK(cudaFuncSetAttribute(k_linear_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (int)((M + TC_M - 1) / TC_M);
+    const int per_sm = (smem <= 100 * 1024) ? 2 : 1;
+    int grid = sm_count() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    k_linear_fwd_tc<<<grid, TC_THREADS, smem, as_stream(stream)>>>(X, ldx, W, bias, Y, ldy, (int)M, N, K, relu, cols);
+    B2R_LAUNCH_OK("k_linear_fwd_tc");
+    return 0;
+}

@@ -527,6 +527,20 @@ def linear_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], r
     return y
 
 
+def linear_fwd_tc(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+    """same as linear_fwd on the tcgen05 tensor cores (TF32 hi/lo split, fp32-class accuracy); raises for shapes
+    outside the kernel's class"""
+    _need_cuda(x, W)
+    M, ldx = _rows_ld(x)
+    N, K = W.shape
+    W = _f32c(W, "W")
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    L = _lib.load()
+    _lib.check(L.b2r_linear_fwd_tc(_p(x), ldx, _p(W), _p(bias), _p(y), N, M, N, K, 1 if relu else 0, _stream()),
+               "b2r_linear_fwd_tc")
+    return y
+
+
 def linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, y_relu: Optional[torch.Tensor],
                need_dx: bool, need_dw: bool, need_db: bool):
     """gradients of y = act(x W^T + b) given dy; y_relu = saved post-ReLU output (None when no ReLU)."""
