@@ -198,6 +198,10 @@ B2R_API int b2r_linear_fwd(const float* X, int ldx, const float* W, const float*
  * B2R_E_UNSUPPORTED outside that class. */
 B2R_API int b2r_linear_fwd_tc(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy,
                       int64_t M, int N, int K, int relu, b2r_stream_t stream);
+/* general form: x_mask (same layout as X, may be NULL) zeroes X where x_mask <= 0 -- with X = dY, x_mask = the layer's
+ * saved ReLU output and W = the transposed weight this is the input gradient dX = (dY * [y > 0]) W of a Linear layer */
+B2R_API int b2r_linear_tc(const float* X, int ldx, const float* x_mask, const float* W, const float* bias, float* Y,
+                  int ldy, int64_t M, int N, int K, int relu, b2r_stream_t stream);
 B2R_API int b2r_linear_bwd_input(const float* dY, int lddy, const float* relu_out, const float* W, float* dX, int lddx,
                          int64_t M, int N, int K, b2r_stream_t stream);
 B2R_API size_t b2r_linear_bwd_weight_workspace_bytes(int64_t M, int N, int K);

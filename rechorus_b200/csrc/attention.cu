@@ -252,11 +252,18 @@ k_small_table_partial(const float* __restrict__ src, int ld, const int64_t* __re
     for (int e = threadIdx.x; e < n_rows * d; e += 256) out[e] = tab[e];
 }
 
-__global__ void k_reduce_chunks_fwd(const float* __restrict__ part, int64_t size, int chunks, float* __restrict__ out) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (int64_t)gridDim.x * blockDim.x) {
+// fixed-order sum over the partial tables: 8 lanes per element (chunks c, c+8, ...), then a fixed shuffle tree
+__global__ void __launch_bounds__(256)
+k_reduce_chunks_fwd(const float* __restrict__ part, int64_t size, int chunks, float* __restrict__ out) {
+    const int cl = threadIdx.x & 7;
+    for (int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3); i < ((size + 31) / 32) * 32; i += (int64_t)gridDim.x * 32) {
         float a = 0.f;
-        for (int c = 0; c < chunks; ++c) a += part[(int64_t)c * size + i];
-        out[i] = a;
+        if (i < size)
+            for (int c = cl; c < chunks; c += 8) a += part[(int64_t)c * size + i];
+        a += __shfl_xor_sync(B2R_FULL_MASK, a, 1);
+        a += __shfl_xor_sync(B2R_FULL_MASK, a, 2);
+        a += __shfl_xor_sync(B2R_FULL_MASK, a, 4);
+        if (cl == 0 && i < size) out[i] = a;
     }
 }
 
@@ -294,7 +301,7 @@ static int capped_grid(int64_t need, int per_sm) {
     return (int)(g < 1 ? 1 : g);
 }
 
-constexpr int kSmallTableRows = 1024;
+constexpr int kSmallTableRows = 256;
 
 }  // namespace b2r
 
@@ -388,7 +395,7 @@ extern "C" int b2r_small_table_grad(const float* src, int ld, const int64_t* ids
     k_small_table_partial<<<ctas, 256, smem, s>>>(src, ld, ids, n, n_rows, d, kSmallTableRows, static_cast<float*>(ws));
     B2R_LAUNCH_OK("k_small_table_partial");
     const int64_t size = (int64_t)n_rows * d;
-    k_reduce_chunks_fwd<<<(int)((size + 255) / 256), 256, 0, s>>>(static_cast<float*>(ws), size, ctas, dense_out);
+    k_reduce_chunks_fwd<<<(int)((size + 31) / 32), 256, 0, s>>>(static_cast<float*>(ws), size, ctas, dense_out);
     B2R_LAUNCH_OK("k_reduce_chunks");
     return 0;
 }

@@ -118,21 +118,30 @@ k_gemm(const float* __restrict__ A, int lda, const float* __restrict__ amask, co
     }
 }
 
-// out[i] = sum over chunks (ascending) of part[c][i]   -- fixed order, one thread per element
+// out[i] = sum over chunks of part[c][i] in a fixed order: 8 lanes per output element each add chunks c, c+8, ...
+// (ascending), then the 8 lane sums are combined by a fixed shuffle tree -> deterministic and 8x more parallel than
+// one thread per element
 __global__ void __launch_bounds__(256)
 k_reduce_chunks(const float* __restrict__ part, int64_t size, int chunks, float* __restrict__ out0, int64_t n0,
                 float* __restrict__ out1) {
     // element i of a [rows, cols+1]-shaped partial: column cols (the ones column) goes to out1 (bias grad)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cl = threadIdx.x & 7;
+    for (int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 3); i < ((size + 31) / 32) * 32; i += (int64_t)gridDim.x * 32) {
         float a = 0.f;
-        for (int c = 0; c < chunks; ++c) a += part[(int64_t)c * size + i];
-        if (out1 == nullptr) {
-            out0[i] = a;
-        } else {
-            const int64_t cols1 = n0 + 1;               // n0 = real columns
-            const int64_t r = i / cols1, cidx = i % cols1;
-            if (cidx < n0) out0[r * n0 + cidx] = a;
-            else out1[r] = a;
+        if (i < size)
+            for (int c = cl; c < chunks; c += 8) a += part[(int64_t)c * size + i];
+        a += __shfl_xor_sync(B2R_FULL_MASK, a, 1);
+        a += __shfl_xor_sync(B2R_FULL_MASK, a, 2);
+        a += __shfl_xor_sync(B2R_FULL_MASK, a, 4);
+        if (cl == 0 && i < size) {
+            if (out1 == nullptr) {
+                out0[i] = a;
+            } else {
+                const int64_t cols1 = n0 + 1;               // n0 = real columns
+                const int64_t r = i / cols1, cidx = i % cols1;
+                if (cidx < n0) out0[r * n0 + cidx] = a;
+                else out1[r] = a;
+            }
         }
     }
 }
@@ -246,7 +255,7 @@ static int gemm_launch(int a_mode, int b_mode, const float* A, int lda, const fl
     return 0;
 }
 
-constexpr int kDwChunk = 2048;   // rows of the batch dimension per dW partial
+constexpr int kDwChunk = 512;    // rows of the batch dimension per dW partial (>= 400 CTAs at B*L = 204,800)
 
 }  // namespace b2r
 
@@ -295,7 +304,7 @@ extern "C" int b2r_linear_bwd_weight(const float* dY, int lddy, const float* rel
                          0, ones, s);
     if (rc != 0) return rc;
     const int64_t size = (int64_t)N * Kc;
-    k_reduce_chunks<<<(int)((size + 255) / 256), 256, 0, s>>>(part, size, chunks, dW, K, ones ? dbias : nullptr);
+    k_reduce_chunks<<<(int)((size + 31) / 32), 256, 0, s>>>(part, size, chunks, dW, K, ones ? dbias : nullptr);
     B2R_LAUNCH_OK("k_reduce_chunks");
     return 0;
 }
@@ -341,9 +350,9 @@ extern "C" int b2r_add_layernorm_bwd(const float* dy, const float* x, const floa
     float* pb = pg + (size_t)ctas * d;
     k_add_layernorm_bwd<<<ctas, 256, 0, s>>>(dy, x, res, gamma, mean, rstd, dz, pg, pb, rows, d, rpc);
     B2R_LAUNCH_OK("k_add_layernorm_bwd");
-    k_reduce_chunks<<<(d + 255) / 256, 256, 0, s>>>(pg, d, ctas, dgamma, 0, nullptr);
+    k_reduce_chunks<<<(d + 31) / 32, 256, 0, s>>>(pg, d, ctas, dgamma, 0, nullptr);
     B2R_LAUNCH_OK("k_reduce_chunks");
-    k_reduce_chunks<<<(d + 255) / 256, 256, 0, s>>>(pb, d, ctas, dbeta, 0, nullptr);
+    k_reduce_chunks<<<(d + 31) / 32, 256, 0, s>>>(pb, d, ctas, dbeta, 0, nullptr);
     B2R_LAUNCH_OK("k_reduce_chunks");
     return 0;
 }

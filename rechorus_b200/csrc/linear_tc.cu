@@ -85,27 +85,30 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split 4 floats into TF32-truncated high parts and exact remainders, store both at the swizzled chunk position
+// round to the nearest TF32 value (10 explicit mantissa bits): the hardware truncates the low 13 bits of what it is
+// given, so operands are pre-rounded here and arrive exactly representable
+__device__ __forceinline__ float tc_rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+// split 4 floats into hi = rn_tf32(x) and lo = rn_tf32(x - hi)  (|x - hi - lo| <= 2^-23 |x|), store both at the
+// swizzled chunk position
 __device__ __forceinline__ void tc_store_split(char* hi_base, char* lo_base, int row, int chunk, const float4& v) {
     const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) * 16);
     float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    h.x = tc_rn_tf32(v.x); h.y = tc_rn_tf32(v.y); h.z = tc_rn_tf32(v.z); h.w = tc_rn_tf32(v.w);
+    l.x = tc_rn_tf32(v.x - h.x); l.y = tc_rn_tf32(v.y - h.y); l.z = tc_rn_tf32(v.z - h.z); l.w = tc_rn_tf32(v.w - h.w);
     *reinterpret_cast<float4*>(hi_base + off) = h;
     *reinterpret_cast<float4*>(lo_base + off) = l;
 }
 
 // dynamic shared memory (1024-byte aligned): A_hi[KS][128*128B] A_lo[...] B_hi[KS][N*128B] B_lo[...]
+template <int KS>
 __global__ void __launch_bounds__(TC_THREADS)
-k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
-                float* __restrict__ Y, int ldy, int M, int N, int K, int relu, int tmem_cols) {
+k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ amask, const float* __restrict__ W,
+                const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int N, int relu, int tmem_cols) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_sh;
-    const int KS = K / 32;                                  // 128-byte K slabs
+    constexpr int K = KS * 32;                              // KS 128-byte K slabs
     const size_t a_slab = (size_t)TC_M * 128, b_slab = (size_t)N * 128;
     // swizzle-128B operand tiles need 1024-byte aligned bases: align by hand (the launch adds 1 KB of slack)
     char* A_hi = reinterpret_cast<char*>(smem_raw) + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -140,12 +143,32 @@ k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ 
     const int ntiles = (M + TC_M - 1) / TC_M;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int m0 = tile * TC_M;
-        // X tile -> A_hi / A_lo
-        for (int e = tid; e < TC_M * KS * 8; e += TC_THREADS) {
-            const int c = e % 8, s = (e / 8) % KS, r = e / (8 * KS);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + r < M) v = ld_row4(X + (size_t)(m0 + r) * ldx + s * 32 + c * 4);
-            tc_store_split(A_hi + s * a_slab, A_lo + s * a_slab, r, c, v);
+        // X tile -> A_hi / A_lo: all 8*KS 128-bit loads of a thread are issued before the first use
+        {
+            float4 v[8 * KS];
+#pragma unroll
+            for (int i = 0; i < 8 * KS; ++i) {
+                const int e = i * TC_THREADS + tid;
+                const int c = e % 8, s = (e / 8) % KS, r = e / (8 * KS);
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m0 + r < M) {
+                    const size_t g = (size_t)(m0 + r) * ldx + s * 32 + c * 4;
+                    v[i] = ld_row4(X + g);
+                    if (amask != nullptr) {                          // ReLU backward: keep dY where the saved output > 0
+                        const float4 mk = ld_row4(amask + g);
+                        v[i].x = mk.x > 0.f ? v[i].x : 0.f;
+                        v[i].y = mk.y > 0.f ? v[i].y : 0.f;
+                        v[i].z = mk.z > 0.f ? v[i].z : 0.f;
+                        v[i].w = mk.w > 0.f ? v[i].w : 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8 * KS; ++i) {
+                const int e = i * TC_THREADS + tid;
+                const int c = e % 8, s = (e / 8) % KS, r = e / (8 * KS);
+                tc_store_split(A_hi + s * a_slab, A_lo + s * a_slab, r, c, v[i]);
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async proxy (UMMA)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -204,6 +227,11 @@ using namespace b2r;
 // returns B2R_E_UNSUPPORTED for shapes outside the tensor-core kernel's class (callers fall back to b2r_linear_fwd)
 extern "C" int b2r_linear_fwd_tc(const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int64_t M,
                                  int N, int K, int relu, b2r_stream_t stream) {
+    return b2r_linear_tc(X, ldx, nullptr, W, bias, Y, ldy, M, N, K, relu, stream);
+}
+
+extern "C" int b2r_linear_tc(const float* X, int ldx, const float* x_mask, const float* W, const float* bias, float* Y,
+                             int ldy, int64_t M, int N, int K, int relu, b2r_stream_t stream) {
     B2R_REQUIRE(X && W && Y, B2R_E_BADARG, "b2r_linear_fwd_tc: null pointer");
     if (!(K % 32 == 0 && K >= 32 && K <= 128 && N % 16 == 0 && N >= 16 && N <= 256 && M > 0 && M <= 0x7fffffff &&
           ldx % 4 == 0 && ldy % 4 == 0 && aligned16(X) && aligned16(W) && aligned16(Y)))
@@ -214,12 +242,18 @@ extern "C" int b2r_linear_fwd_tc(const float* X, int ldx, const float* W, const 
     if (smem > 200 * 1024) return set_error(B2R_E_UNSUPPORTED, "b2r_linear_fwd_tc: %zu B of shared memory needed", smem);
     int cols = 32;
     while (cols < N) cols <<= 1;
-    B2R_CUDA_OK(cudaFuncSetAttribute(k_linear_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = (int)((M + TC_M - 1) / TC_M);
     const int per_sm = (smem <= 100 * 1024) ? 2 : 1;
     int grid = sm_count() * per_sm;
     if (grid > ntiles) grid = ntiles;
-    k_linear_fwd_tc<<<grid, TC_THREADS, smem, as_stream(stream)>>>(X, ldx, W, bias, Y, ldy, (int)M, N, K, relu, cols);
+#define B2R_TC(KSV)                                                                                    \
+    do {                                                                                               \
+        B2R_CUDA_OK(cudaFuncSetAttribute(k_linear_fwd_tc<KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_linear_fwd_tc<KSV><<<grid, TC_THREADS, smem, as_stream(stream)>>>(X, ldx, x_mask, W, bias, Y, ldy, (int)M, N, relu, \
+                                                                            cols);                     \
+    } while (0)
+    if (KS == 1) B2R_TC(1); else if (KS == 2) B2R_TC(2); else if (KS == 3) B2R_TC(3); else B2R_TC(4);
+#undef B2R_TC
     B2R_LAUNCH_OK("k_linear_fwd_tc");
     return 0;
 }

@@ -80,6 +80,8 @@ SIGNATURES = {
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b2r_linear_fwd_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "b2r_linear_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "b2r_linear_bwd_input": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "b2r_linear_bwd_weight_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
