@@ -88,6 +88,12 @@ B2R_API int b2r_gather_rows_strided(const float* T, const int64_t* ids, int64_t 
 B2R_API int b2r_pairdot_fwd(const float* Q, const int64_t* qidx, int64_t n_q, const float* T, const int64_t* rows,
                     int64_t n_t, float* out, int64_t n, int d, int32_t* err_flag, b2r_stream_t stream);
 
+/* out[key[e],:] = sum over each run of consecutive valid pairs sharing key[e] of coef[e] * T[rows[e],:]  (rows < 0 =
+ * unused slot; every key occupies one contiguous run, as the stable owner-bucketing of the sharded exchange
+ * guarantees; out rows without pairs are left untouched).  The shard owner's half of dQ = sum_c g * I[id]. */
+B2R_API int b2r_pair_runs_sum(const int64_t* key, const int64_t* rows, const float* coef, const float* T, int64_t n_t,
+                      float* out, int64_t n_out, int64_t n, int d, b2r_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * BPR loss + closed-form gradient (models/BaseModel.py:175-189; formula SURVEY.md A.4).
  * pred [B,C] (column 0 = positive).  loss_out: 1 float.  grad_pred [B,C] = d loss / d pred (may be NULL).

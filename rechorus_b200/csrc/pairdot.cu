@@ -73,9 +73,77 @@ k_pairdot_fwd_generic(const float* __restrict__ Q, const int64_t* __restrict__ q
     }
 }
 
+// out[key[e], :] = sum over the run of consecutive valid elements sharing key[e] of coef[e] * T[rows[e], :]
+// (rows[e] < 0 = unused slot).  The shard owner's half of dQ = sum_c g * I[id]: the pairs a rank receives from one
+// source arrive grouped by sample (the sender bucketed them with a stable partition), so every (source, sample) is one
+// contiguous run and no sort is needed; a lane group owns the run whose first element it lands on and walks it in
+// order (4 independent partial sums, combined in a fixed order).  Every output row is written at most once; rows
+// without elements keep what the caller put there (zeros).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_pair_runs_sum(const int64_t* __restrict__ key, const int64_t* __restrict__ rows, const float* __restrict__ coef,
+                const float* __restrict__ T, int64_t n_t, float* __restrict__ out, int64_t n_out, int64_t n) {
+    constexpr int D = LPR * 4;
+    constexpr int GPC = 256 / LPR;
+    const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+    for (int64_t e = (int64_t)blockIdx.x * GPC + grp; e < n; e += (int64_t)gridDim.x * GPC) {
+        if (rows[e] < 0) continue;
+        const int64_t k = key[e];
+        if (e > 0 && rows[e - 1] >= 0 && key[e - 1] == k) continue;          // not the first element of its run
+        if (k < 0 || k >= n_out) continue;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        int64_t j = e;
+        for (;;) {
+            int64_t r[4];
+            float c[4];
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                r[u] = -1;
+                c[u] = 0.f;
+                if (cnt == u && j < n && rows[j] >= 0 && key[j] == k) {
+                    r[u] = rows[j] < n_t ? rows[j] : 0;
+                    c[u] = coef[j];
+                    ++j;
+                    ++cnt;
+                }
+            }
+            if (cnt == 0) break;
+            if (r[0] >= 0) fma4(a0, c[0], ld_row4(T + r[0] * D + sub * 4));
+            if (r[1] >= 0) fma4(a1, c[1], ld_row4(T + r[1] * D + sub * 4));
+            if (r[2] >= 0) fma4(a2, c[2], ld_row4(T + r[2] * D + sub * 4));
+            if (r[3] >= 0) fma4(a3, c[3], ld_row4(T + r[3] * D + sub * 4));
+            if (cnt < 4) break;
+        }
+        a0.x = (a0.x + a1.x) + (a2.x + a3.x);
+        a0.y = (a0.y + a1.y) + (a2.y + a3.y);
+        a0.z = (a0.z + a1.z) + (a2.z + a3.z);
+        a0.w = (a0.w + a1.w) + (a2.w + a3.w);
+        st4(out + k * D + sub * 4, a0);
+    }
+}
+
 }  // namespace b2r
 
 using namespace b2r;
+
+extern "C" int b2r_pair_runs_sum(const int64_t* key, const int64_t* rows, const float* coef, const float* T, int64_t n_t,
+                                 float* out, int64_t n_out, int64_t n, int d, b2r_stream_t stream) {
+    B2R_REQUIRE(key && rows && coef && T && out, B2R_E_BADARG, "b2r_pair_runs_sum: null pointer");
+    B2R_REQUIRE(d == 32 || d == 64 || d == 128, B2R_E_UNSUPPORTED, "b2r_pair_runs_sum: d=%d (have 32, 64, 128)", d);
+    if (n <= 0) return 0;
+    cudaStream_t s = as_stream(stream);
+    const int64_t cap = (int64_t)sm_count() * 16;
+#define B2R_PR(LPR)                                                                                    \
+    do {                                                                                               \
+        const int64_t need = (n + 256 / LPR - 1) / (256 / LPR);                                        \
+        k_pair_runs_sum<LPR><<<(int)(need < cap ? need : cap), 256, 0, s>>>(key, rows, coef, T, n_t, out, n_out, n); \
+    } while (0)
+    if (d == 32) B2R_PR(8); else if (d == 64) B2R_PR(16); else B2R_PR(32);
+#undef B2R_PR
+    B2R_LAUNCH_OK("k_pair_runs_sum");
+    return 0;
+}
 
 extern "C" int b2r_pairdot_fwd(const float* Q, const int64_t* qidx, int64_t n_q, const float* T, const int64_t* rows,
                                int64_t n_t, float* out, int64_t n, int d, int32_t* err_flag, b2r_stream_t stream) {

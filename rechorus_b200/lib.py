@@ -53,6 +53,8 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     "b2r_pairdot_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "b2r_pair_runs_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.c_int64, C.c_int, C.c_void_p]),
     "b2r_bpr_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b2r_plan_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "b2r_plan_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -139,6 +139,17 @@ def pairdot(Q: torch.Tensor, qidx: torch.Tensor, T: torch.Tensor, rows: torch.Te
     return out
 
 
+def pair_runs_sum(out: torch.Tensor, key: torch.Tensor, rows: torch.Tensor, coef: torch.Tensor, T: torch.Tensor) -> None:
+    """out[key[e]] = sum over each contiguous run of valid pairs with that key of coef[e] * T[rows[e]]
+    (b2r_pair_runs_sum; rows < 0 = unused slot)"""
+    _need_cuda(out, key, rows, coef, T)
+    key, rows = _i64c(key.reshape(-1), "key"), _i64c(rows.reshape(-1), "rows")
+    coef, T = _f32c(coef.reshape(-1), "coef"), _f32c(T, "T")
+    L = _lib.load()
+    _lib.check(L.b2r_pair_runs_sum(_p(key), _p(rows), _p(coef), _p(T), T.shape[0], _p(out), out.shape[0], rows.numel(),
+                                   T.shape[1], _stream()), "b2r_pair_runs_sum")
+
+
 def bpr_loss_and_grad(pred: torch.Tensor, want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """BaseModel.py:175-189 value and closed-form d loss / d pred in one pass."""
     _need_cuda(pred)

@@ -52,12 +52,10 @@ class CudaBackend:
         from . import ops
         return ops.bpr_loss_and_grad(pred)
 
-    def add_rows(self, dense, ids, src, coef, src_id):
-        """dense[ids[p]] += coef[p] * src[src_id[p]] for ids[p] >= 0 (deterministic)"""
+    def sum_runs(self, out, key, rows, coef, T):
+        """out[key[e]] = sum over each contiguous run of valid (rows >= 0) pairs with that key of coef[e] * T[rows[e]]"""
         from . import ops
-        n = ids.numel()
-        plan = ops.make_plan(ids, dense.shape[0], dense.shape[1], ignore_id=-1, ignore_n=n)
-        plan.add_to_dense(dense, [ops.Source(src=src, n=n, coef=coef, src_id=src_id)])
+        ops.pair_runs_sum(out, key, rows, coef, T)
 
     def optimizer_rows(self, W, state, ids, src, coef, src_id, opt):
         """row-sparse optimizer on W for the rows ids[p] >= 0 with gradient sum_p coef[p] * src[src_id[p]]"""
@@ -74,10 +72,19 @@ class CudaBackend:
 
 def _bucket_by_owner(owner: torch.Tensor, world: int):
     """stable partition of positions by owner: returns (order, owner_sorted, rank_within_owner, counts)"""
-    order = torch.argsort(owner, stable=True)
-    owner_sorted = owner[order]
-    counts = torch.bincount(owner, minlength=world)
-    starts = torch.cumsum(counts, 0) - counts
+    if world == 1:
+        n = owner.numel()
+        ar = torch.arange(n, device=owner.device)
+        return ar, torch.zeros_like(owner), ar, torch.full((1,), n, dtype=torch.int64, device=owner.device)
+    # 8-bit keys: one radix pass instead of eight (W <= 255 ranks on one box)
+    key_sorted, order = torch.sort(owner.to(torch.uint8), stable=True)
+    owner_sorted = key_sorted.to(torch.int64)
+    # segment starts by binary search in the sorted keys (a histogram of 1 M values into <= 8 bins is all atomics)
+    bounds = torch.searchsorted(key_sorted, torch.arange(world + 1, device=owner.device, dtype=torch.uint8).clamp(max=255)
+                                if world < 255 else torch.arange(world + 1, device=owner.device), right=False)
+    bounds[-1] = owner.numel()
+    starts = bounds[:-1]
+    counts = bounds[1:] - bounds[:-1]
     rank = torch.arange(owner.numel(), device=owner.device) - starts[owner_sorted]
     return order, owner_sorted, rank, counts
 
@@ -160,14 +167,16 @@ class ShardedBPRMF:
         ord_i, own_is, rank_i, counts_i = _bucket_by_owner(own_i, W)
         cap = self.capacity(n)
         torch._assert_async(counts_i.max() <= cap)                                # ids too skewed for cap_factor
-        send_pairs = torch.full((W, cap, 2), -1, dtype=torch.int64, device=dev)
+        if B >= (1 << 21):
+            raise ValueError("per-rank batch too large for the packed (row, sample) exchange format")
+        send_pairs = torch.full((W, cap), -1, dtype=torch.int64, device=dev)      # (local row << 21) | sample index
         keep_rank = rank_i.clamp(max=cap - 1)
-        send_pairs[own_is, keep_rank, 0] = (flat - own_i * self.rows_i)[ord_i]
-        send_pairs[own_is, keep_rank, 1] = torch.div(ord_i, C, rounding_mode="floor")
-        recv_pairs = self._a2a(send_pairs)                                        # [W(src), cap, 2]
-        rows = recv_pairs[:, :, 0].contiguous()
+        send_pairs[own_is, keep_rank] = ((flat - own_i * self.rows_i)[ord_i] << 21) | torch.div(ord_i, C, rounding_mode="floor")
+        recv_pairs = self._a2a(send_pairs)                                        # [W(src), cap]
+        rows = recv_pairs >> 21                                                   # -1 stays -1 (arithmetic shift)
         src_base = (torch.arange(W, device=dev) * B).view(W, 1)
-        qidx = (recv_pairs[:, :, 1].clamp(min=0) + src_base).contiguous()         # row of q_all
+        qidx = (recv_pairs & ((1 << 21) - 1)) + src_base                          # row of q_all (garbage where rows < 0)
+        qidx = torch.where(rows >= 0, qidx, torch.zeros_like(qidx))
         # D. owners score, scores travel back
         sc_recv = self._a2a(be.pairdot(q_all, qidx, self.I, rows).view(W, cap))   # [W(owner), cap]
         pred = torch.empty(n, dtype=torch.float32, device=dev)
@@ -189,12 +198,11 @@ class ShardedBPRMF:
         g_send[st["own_is"], st["keep_rank"]] = g.reshape(-1)[st["ord_i"]]
         g_recv = self._a2a(g_send).reshape(-1)                                    # [W*cap], 0 in unused slots
         rows, qidx, q_all = st["rows"].reshape(-1), st["qidx"].reshape(-1), st["q_all"]
-        valid_rows = rows.clamp(min=0)
         self.t += 1
         opt_i = be.make_opt(self.opt_name, self.lr, self.betas, self.eps, self.l2, self.t)
         # G. dQ partials for every (src, sample) this owner served: dQ[src*B+b] += g * I[row]   (before I moves)
         dq_part = torch.zeros((W * B, d), dtype=torch.float32, device=dev)
-        be.add_rows(dq_part, torch.where(rows >= 0, qidx, torch.full_like(qidx, -1)), self.I, g_recv, valid_rows)
+        be.sum_runs(dq_part, qidx, rows, g_recv, self.I)
         # H. item shard: fused row-sparse optimizer, gradient row = sum g * q_all[qidx]
         be.optimizer_rows(self.I, self.state_i, rows, q_all, g_recv, qidx, opt_i)
         # I. home ranks get their samples' dQ summed over the owners

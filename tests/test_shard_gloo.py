@@ -29,13 +29,18 @@ class CpuStandIn:
         loss.backward()
         return loss.detach(), p.grad
 
-    def add_rows(self, dense, ids, src, coef, src_id):
-        keep = ids >= 0
-        dense.index_add_(0, ids[keep], coef[keep].unsqueeze(1) * src[src_id[keep]])
+    def sum_runs(self, out, key, rows, coef, T):
+        keep = rows >= 0
+        # every key must occupy ONE contiguous run among the valid pairs (what the CUDA kernel relies on)
+        k = key[keep]
+        change = torch.nonzero(k[1:] != k[:-1]).numel() + 1 if k.numel() else 0
+        assert change == torch.unique(k).numel()
+        out.index_add_(0, k, coef[keep].unsqueeze(1) * T[rows[keep]])
 
     def optimizer_rows(self, W, state, ids, src, coef, src_id, opt):
         g = torch.zeros_like(W)
-        self.add_rows(g, ids, src, coef, src_id)
+        keep = ids >= 0
+        g.index_add_(0, ids[keep], coef[keep].unsqueeze(1) * src[src_id[keep]])
         touched = torch.zeros(W.shape[0], dtype=torch.bool)
         touched[ids[ids >= 0]] = True
         W[touched] -= opt["lr"] * (g[touched] + opt["wd"] * W[touched])          # SGD is enough for the wiring test

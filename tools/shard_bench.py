@@ -22,7 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n_items", type=int, default=100_000_000)
     ap.add_argument("--n_users", type=int, default=1_000_000)
-    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--emb", type=int, default=128)
     ap.add_argument("--B", type=int, default=4096)
     ap.add_argument("--K", type=int, default=255)
     ap.add_argument("--steps", type=int, default=20)
@@ -38,7 +38,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from rechorus_b200 import ops
     from rechorus_b200.shard import ShardedBPRMF
-    m = ShardedBPRMF(a.n_users, a.n_items, a.d, dev, optimizer=a.optimizer, lr=1e-3, init_std=0.1 if a.check else 0.01)
+    m = ShardedBPRMF(a.n_users, a.n_items, a.emb, dev, optimizer=a.optimizer, lr=1e-3, init_std=0.1 if a.check else 0.01)
     C = a.K + 1
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = [(torch.randint(1, a.n_users, (a.B,), device=dev, generator=g),
@@ -47,8 +47,8 @@ def main():
         uid, iid = pool[0]
         pred, _ = m.scores(uid, iid)
         if world > 1:
-            U = torch.empty(world * m.rows_u, a.d, device=dev); dist.all_gather_into_tensor(U, m.U)
-            I = torch.empty(world * m.rows_i, a.d, device=dev); dist.all_gather_into_tensor(I, m.I)
+            U = torch.empty(world * m.rows_u, a.emb, device=dev); dist.all_gather_into_tensor(U, m.U)
+            I = torch.empty(world * m.rows_i, a.emb, device=dev); dist.all_gather_into_tensor(I, m.I)
         else:
             U, I = m.U, m.I
         ref = torch.einsum("bd,bcd->bc", U[uid], I[iid])
@@ -90,7 +90,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "training samples/sec (user x (1+neg))", "value": world * a.B * C / (ms * 1e-3),
                           "unit": "user*item/s", "n_gpus": world, "ms_per_step": ms, "scaling": "weak",
-                          "config": {"workload": f"sharded BPRMF d={a.d} n_items={a.n_items} n_users={a.n_users} "
+                          "config": {"workload": f"sharded BPRMF d={a.emb} n_items={a.n_items} n_users={a.n_users} "
                                                  f"B={a.B}/GPU K={a.K}", "parallelism": f"row-range shards x{world}, score routing",
                                      "optimizer": a.optimizer + " (row-sparse)"},
                           "loss": float(loss), "mem_GB": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
