@@ -311,8 +311,17 @@ def run_ours(args, rank, world, local_rank):
     alg = {k_: v for k_, v in alg.items() if k_ in kern_ms}
     dom = max(alg, key=lambda k_: kern_ms[k_])
     achieved = alg[dom] / (kern_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+    traffic = None                              # DRAM bytes per launch of that kernel from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and args.workload == "c2":
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
+    cuda_names = {"segment_adam_items": "k_apply_sorted<16,2> (item table: segment reduce + Adam)",
+                  "fused_score_loss_bwd": "k_bprmf_fused<16,8,3>", "segment_adam_users": "k_apply_sorted<16,2> (user table)",
+                  "score_fwd": "k_rowdot_fwd", "score_bwd_query": "k_rowdot_bwd_query"}
+    roofline = {"bound": "hbm", "kernel": dom, "cuda_kernel": cuda_names.get(dom, dom), "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "peak_source": peak_src,
                 "alg_bytes_per_launch": int(alg[dom]), "kernel_ms": round(kern_ms[dom], 5)}
     kernels = {k_: {"ms": round(v, 5), "GBps": round(alg[k_] / (v * 1e-3) / 1e9, 1) if k_ in alg else None}
                for k_, v in kern_ms.items()}

@@ -76,50 +76,87 @@ k_pairdot_fwd_generic(const float* __restrict__ Q, const int64_t* __restrict__ q
 // out[key[e], :] = sum over the run of consecutive valid elements sharing key[e] of coef[e] * T[rows[e], :]
 // (rows[e] < 0 = unused slot).  The shard owner's half of dQ = sum_c g * I[id]: the pairs a rank receives from one
 // source arrive grouped by sample (the sender bucketed them with a stable partition), so every (source, sample) is one
-// contiguous run and no sort is needed; a lane group owns the run whose first element it lands on and walks it in
-// order (4 independent partial sums, combined in a fixed order).  Every output row is written at most once; rows
-// without elements keep what the caller put there (zeros).
+// contiguous run and no sort is needed.  A lane group scans a block of LPR consecutive elements at a time (one
+// element's metadata per lane, coalesced), finds the runs that START in its block with a ballot, and walks each of
+// them in element order -- metadata travels by shuffle, only the table rows are loaded in the walk.  Every output row
+// is written at most once (fixed summation order); rows without elements keep what the caller put there (zeros).
 template <int LPR>
 __global__ void __launch_bounds__(256)
 k_pair_runs_sum(const int64_t* __restrict__ key, const int64_t* __restrict__ rows, const float* __restrict__ coef,
                 const float* __restrict__ T, int64_t n_t, float* __restrict__ out, int64_t n_out, int64_t n) {
     constexpr int D = LPR * 4;
     constexpr int GPC = 256 / LPR;
+    const int lane = threadIdx.x & 31;
     const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
-    for (int64_t e = (int64_t)blockIdx.x * GPC + grp; e < n; e += (int64_t)gridDim.x * GPC) {
-        if (rows[e] < 0) continue;
-        const int64_t k = key[e];
-        if (e > 0 && rows[e - 1] >= 0 && key[e - 1] == k) continue;          // not the first element of its run
-        if (k < 0 || k >= n_out) continue;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-        int64_t j = e;
-        for (;;) {
-            int64_t r[4];
-            float c[4];
-            int cnt = 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                r[u] = -1;
-                c[u] = 0.f;
-                if (cnt == u && j < n && rows[j] >= 0 && key[j] == k) {
-                    r[u] = rows[j] < n_t ? rows[j] : 0;
-                    c[u] = coef[j];
-                    ++j;
-                    ++cnt;
-                }
-            }
-            if (cnt == 0) break;
-            if (r[0] >= 0) fma4(a0, c[0], ld_row4(T + r[0] * D + sub * 4));
-            if (r[1] >= 0) fma4(a1, c[1], ld_row4(T + r[1] * D + sub * 4));
-            if (r[2] >= 0) fma4(a2, c[2], ld_row4(T + r[2] * D + sub * 4));
-            if (r[3] >= 0) fma4(a3, c[3], ld_row4(T + r[3] * D + sub * 4));
-            if (cnt < 4) break;
+    const int goff = lane - sub;                                           // first lane of this group in its warp
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << goff);
+    const int64_t nblocks = (n + LPR - 1) / LPR;
+    for (int64_t blk = (int64_t)blockIdx.x * GPC + grp; blk < nblocks; blk += (int64_t)gridDim.x * GPC) {
+        const int64_t e0 = blk * LPR;
+        int64_t b_row = -1, b_key = -1;
+        float b_coef = 0.f;
+        if (e0 + sub < n) {
+            b_row = rows[e0 + sub];
+            b_key = key[e0 + sub];
+            b_coef = coef[e0 + sub];
         }
-        a0.x = (a0.x + a1.x) + (a2.x + a3.x);
-        a0.y = (a0.y + a1.y) + (a2.y + a3.y);
-        a0.z = (a0.z + a1.z) + (a2.z + a3.z);
-        a0.w = (a0.w + a1.w) + (a2.w + a3.w);
-        st4(out + k * D + sub * 4, a0);
+        // head of a run: valid, and the previous element is invalid or has another key
+        int64_t p_row = __shfl_up_sync(gmask, b_row, 1, LPR), p_key = __shfl_up_sync(gmask, b_key, 1, LPR);
+        if (sub == 0) {
+            p_row = -1;
+            if (e0 > 0) {
+                p_row = rows[e0 - 1];
+                p_key = key[e0 - 1];
+            }
+        }
+        const bool is_head = b_row >= 0 && b_key >= 0 && b_key < n_out && (p_row < 0 || p_key != b_key);
+        unsigned heads = (__ballot_sync(gmask, is_head) >> goff) & ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u));
+        while (heads) {
+            const int h = __ffs(heads) - 1;
+            heads &= heads - 1;
+            const int64_t k = __shfl_sync(gmask, b_key, h, LPR);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int64_t c_row = b_row, c_key = b_key;                          // metadata of the block being walked
+            float c_coef = b_coef;
+            int start = h;
+            int64_t next = e0 + LPR;
+            for (;;) {
+                const bool mine = (sub >= start) && c_row >= 0 && c_key == k;
+                unsigned in_run = (__ballot_sync(gmask, mine) >> goff) & ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u));
+                in_run >>= start;
+                const int len = (~in_run == 0u) ? 32 - start : __ffs(~in_run) - 1;   // consecutive members from `start`
+                int t = start;
+                for (; t + 4 <= start + len; t += 4) {                      // 4 row loads in flight, added in order
+                    float4 x[4];
+                    float c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int64_t r = __shfl_sync(gmask, c_row, t + u, LPR);
+                        c[u] = __shfl_sync(gmask, c_coef, t + u, LPR);
+                        x[u] = ld_row4(T + (r < n_t ? r : 0) * D + sub * 4);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) fma4(acc, c[u], x[u]);
+                }
+                for (; t < start + len; ++t) {
+                    const int64_t r = __shfl_sync(gmask, c_row, t, LPR);
+                    const float c = __shfl_sync(gmask, c_coef, t, LPR);
+                    fma4(acc, c, ld_row4(T + (r < n_t ? r : 0) * D + sub * 4));
+                }
+                if (start + len < LPR || next >= n) break;                 // run ended inside this block / input ended
+                c_row = -1;
+                c_key = -1;
+                c_coef = 0.f;
+                if (next + sub < n) {
+                    c_row = rows[next + sub];
+                    c_key = key[next + sub];
+                    c_coef = coef[next + sub];
+                }
+                start = 0;
+                next += LPR;
+            }
+            st4(out + k * D + sub * 4, acc);
+        }
     }
 }
 

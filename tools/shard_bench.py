@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--optimizer", type=str, default="Adam")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--torch_profile", action="store_true", help="print a torch.profiler kernel table for 3 steps (rank 0)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
@@ -74,6 +75,14 @@ def main():
     for k in range(a.warmup):
         m.train_step(*pool[k % 4])
     torch.cuda.synchronize()
+    if a.torch_profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for k in range(3):
+                m.train_step(*pool[k % 4])
+            torch.cuda.synchronize()
+        if rank == 0:
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70), flush=True)
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
