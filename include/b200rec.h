@@ -257,6 +257,28 @@ B2R_API int b2r_colscale(const float* a, const float* w, float* out, int64_t row
 B2R_API int b2r_colsum_prod(const float* a, const float* b, float* out, int64_t rows, int d, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Evaluation (row f2): integer ranks of the ground-truth item on the device.
+ *
+ * b2r_gt_rank:        rank[r] = #{c : pred[r*ld + c] >= pred[r*ld]}  -- helpers/BaseRunner.py:63 (column 0 is the
+ *                     ground truth, ties count against it, rank >= 1; NaN compares false as in NumPy).
+ * b2r_rank_histogram: hist[k] = #{r : rank[r] == k} for k <= kmax, hist[kmax+1] = #{rank > kmax}; hist has kmax+2
+ *                     int64 slots.  HR@k and NDCG@k (BaseRunner.py:66-74) are sums over hist[1..k].
+ * b2r_rank_all_items: the test_all protocol (BaseModel.py:194-198: candidates = [target] + arange(1, n_items),
+ *                     scored by a dot product with the query row -- BPRMF.py:42, SASRec.py:81 -- then
+ *                     preds[row, clicked item] = -inf, BaseRunner.py:244-251) without materialising the
+ *                     [B, n_items] score matrix: rank[b] = 1 + #{1 <= j < n_items, (b,j) not masked :
+ *                     <Q[b], I[j]> >= <Q[b], I[target[b]]>}.  Q [B, ldq] are the query rows (user vectors or
+ *                     sequence states), (mask_row[e], mask_item[e]) the n_mask unique (batch row, item id) pairs to
+ *                     exclude, s0 [B] scratch that receives the targets' scores.  The unmasked target column counts
+ *                     (it scores equal to column 0), exactly as in the reference.
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API int b2r_gt_rank(const float* pred, int64_t N, int64_t C, int64_t ld, int64_t* rank, b2r_stream_t stream);
+B2R_API int b2r_rank_histogram(const int64_t* rank, int64_t N, int kmax, int64_t* hist, b2r_stream_t stream);
+B2R_API int b2r_rank_all_items(const float* Q, int ldq, const float* I, const int64_t* target, int B, int64_t n_items,
+                               int d, const int64_t* mask_row, const int64_t* mask_item, int64_t n_mask, float* s0,
+                               int64_t* rank, int32_t* err_flag, b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused BPRMF forward + loss + query-side backward: every candidate row is read from HBM once and stays in
  * registers between scoring and the gradient.  Outputs: grad_pred [B,C] (= d loss / d pred, loss = mean of the
  * per-sample losses), row_loss [B] (per-sample -log S), dQ [B,d] (= sum_c g[b,c] I[iid[b,c]]), pred [B,C]

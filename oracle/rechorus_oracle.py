@@ -242,6 +242,24 @@ def rank_metrics(pred: np.ndarray, topk: Sequence[int], metrics: Sequence[str]) 
     return out
 
 
+def test_all_predictions(q: Tensor, item_table: Tensor, target: Tensor,
+                         clicked: Sequence[Sequence[int]] | None = None) -> np.ndarray:
+    """The test_all protocol for a dot-product model: candidates = [target] + arange(1, n_items)
+    (models/BaseModel.py:194-198), scores = (q[:, None, :] * I[candidates]).sum(-1) (BPRMF.py:42, SASRec.py:81),
+    then preds[row, clicked item id] = -inf (helpers/BaseRunner.py:244-251; the column index IS the item id)."""
+    n_items = item_table.shape[0]
+    cand = torch.cat([target.view(-1, 1), torch.arange(1, n_items).view(1, -1).expand(target.numel(), -1)], dim=1)
+    pred = (q[:, None, :] * F.embedding(cand, item_table)).sum(dim=-1).numpy().copy()
+    if clicked is not None:
+        rows, cols = [], []
+        for i, items in enumerate(clicked):
+            items = list(items)
+            rows.extend([i] * len(items))
+            cols.extend(items)
+        pred[rows, cols] = -np.inf
+    return pred
+
+
 def sample_negatives(user_ids: Sequence[int], clicked: Dict[int, set], n_items: int, num_neg: int,
                      rng: np.random.RandomState) -> np.ndarray:
     """models/BaseModel.py:206-214: uniform over [1, n_items) with rejection against the user's

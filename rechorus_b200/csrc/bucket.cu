@@ -283,6 +283,157 @@ k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const in
     }
 }
 
+// Rows with many contributions (listed by k_bucket_sort): the whole CTA reduces one row -- contribution t goes to
+// group t % GPC, partials are combined in group order -> deterministic.  Normally the list is empty.
+template <int LPR, int MODE>
+__device__ __forceinline__ void apply_long_rows(const uint64_t* __restrict__ pairs, const int* __restrict__ n_long_ptr,
+                                                const uint2* __restrict__ longs, int long_cap, const BSrc& s0,
+                                                const BSrc& s1, float* W, float* M, float* V, float* dense,
+                                                const OptK& opt, float4 (*part)[LPR]) {
+    constexpr int D = LPR * 4;
+    constexpr int GPC = kBT / LPR;
+    const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+    const int n_long = min(*n_long_ptr, long_cap);
+    for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
+        const uint2 e = longs[q];
+        const int j0 = (int)e.x, len = (int)e.y;
+        const int64_t row = (int64_t)(pairs[j0] >> 32);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = grp; t < len; t += GPC) {
+            const float* base;
+            int ld;
+            int64_t r;
+            float c;
+            b_contribution(s0, s1, (uint32_t)pairs[j0 + t], base, ld, r, c);
+            fma4(acc, c, ld4(base + r * ld + sub * 4));
+        }
+        part[grp][sub] = acc;
+        __syncthreads();
+        if (grp == 0) {
+            float4 tot = part[0][sub];
+            for (int g2 = 1; g2 < GPC; ++g2) {
+                const float4 y = part[g2][sub];
+                tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
+            }
+            float4 w, m, v;
+            if (MODE == 2) {
+                w = ld4(W + row * D + sub * 4);
+                if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+                if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+            } else {
+                w = ld4(dense + row * D + sub * 4);
+            }
+            RowIO<LPR>::template finish<MODE>(row, tot, sub, w, m, v, W, M, V, dense, opt);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_apply_sorted_pipe: the same walk with the weight/state rows of a lane group's next S-1 pairs already in flight.
+// The rows are fetched with cp.async (16 B per lane, L1 bypassed) into a per-group ring in shared memory, so the bytes
+// in flight per SM are bounded by shared memory (S * 768 B per group at d=64 with Adam) instead of by the registers
+// that hold load results; the keys of the pair after those are fetched one iteration earlier still.  Every lane
+// reads back only what it copied itself, so cp.async.wait_group is the only synchronisation.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gptr) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int LPR, int S>
+__global__ void __launch_bounds__(kBT)
+k_apply_sorted_pipe(const uint64_t* __restrict__ pairs, const int* __restrict__ n_valid_ptr,
+                    const int* __restrict__ n_long_ptr, const uint2* __restrict__ longs, int long_cap, BSrc s0, BSrc s1,
+                    float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, OptK opt) {
+    constexpr int D = LPR * 4;
+    constexpr int GPC = kBT / LPR;
+    constexpr uint64_t kSkip = ~0ull;            // ring entry of a pair that is not the head of its row
+    extern __shared__ __align__(16) unsigned char pipe_smem[];
+    float4* rows = reinterpret_cast<float4*>(pipe_smem);                       // [S][3][kBT]
+    uint64_t* ring = reinterpret_cast<uint64_t*>(rows + S * 3 * kBT);          // [S][kBT]
+    __shared__ float4 part[GPC][LPR];
+    const int tid = threadIdx.x, sub = tid % LPR, grp = tid / LPR;
+    const int n_valid = *n_valid_ptr;
+    const int stride = gridDim.x * GPC;
+    const int j0 = blockIdx.x * GPC + grp;
+    const int first = blockIdx.x * GPC;
+    const int iters = first < n_valid ? (n_valid - first + stride - 1) / stride : 0;
+    const int sld = opt.state_ld ? opt.state_ld : D;
+
+    uint64_t kc = kSkip;
+    uint32_t kp = 0;
+    auto fetch_keys = [&](int it) {
+        const int j = j0 + it * stride;
+        if (it < iters && j < n_valid) {
+            kc = pairs[j];
+            kp = j > 0 ? (uint32_t)(pairs[j - 1] >> 32) : ~(uint32_t)(kc >> 32);
+        } else {
+            kc = kSkip;
+            kp = 0xffffffffu;
+        }
+    };
+    auto issue = [&](int it) {
+        const int slot = it % S;
+        const uint32_t key = (uint32_t)(kc >> 32);
+        const bool head = key != kp;
+        ring[slot * kBT + tid] = head ? kc : kSkip;
+        if (head) {
+            const int64_t row = (int64_t)key;
+            cp_async16(&rows[(slot * 3 + 0) * kBT + tid], W + row * D + sub * 4);
+            if (opt.kind == 1) cp_async16(&rows[(slot * 3 + 1) * kBT + tid], M + row * sld + sub * 4);
+            if (opt.kind != 0) cp_async16(&rows[(slot * 3 + 2) * kBT + tid], V + row * sld + sub * 4);
+        }
+        cp_async_commit();
+    };
+    for (int it = 0; it < S - 1; ++it) {
+        fetch_keys(it);
+        issue(it);
+    }
+    fetch_keys(S - 1);
+    for (int i = 0; i < iters; ++i) {
+        issue(i + S - 1);
+        fetch_keys(i + S);
+        cp_async_wait<S - 1>();
+        const int slot = i % S;
+        uint64_t cur = ring[slot * kBT + tid];
+        if (cur == kSkip) continue;
+        const uint32_t key = (uint32_t)(cur >> 32);
+        const int64_t row = (int64_t)key;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int len = 0;
+        bool is_long = false;
+        for (int jj = j0 + i * stride;;) {
+            const float* base;
+            int ld;
+            int64_t r;
+            float c;
+            b_contribution(s0, s1, (uint32_t)cur, base, ld, r, c);
+            fma4(acc, c, ld4(base + r * ld + sub * 4));
+            ++len;
+            if (++jj >= n_valid) break;
+            cur = pairs[jj];
+            if ((uint32_t)(cur >> 32) != key) break;
+            if (len >= kLong) {
+                is_long = true;
+                break;
+            }
+        }
+        if (is_long) continue;
+        float4 w = rows[(slot * 3 + 0) * kBT + tid], m, v;
+        if (opt.kind == 1) m = rows[(slot * 3 + 1) * kBT + tid];
+        if (opt.kind != 0) v = rows[(slot * 3 + 2) * kBT + tid];
+        RowIO<LPR>::template finish<2>(row, acc, sub, w, m, v, W, M, V, nullptr, opt);
+    }
+    cp_async_wait<0>();
+    apply_long_rows<LPR, 2>(pairs, n_long_ptr, longs, long_cap, s0, s1, W, M, V, nullptr, opt, part);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // k_apply_sorted: one lane group per pair index; the group whose pair is the first of its row owns the row: it
 // requests the weight/state rows, walks the row's contributions (ascending position), applies the update.
@@ -333,42 +484,7 @@ k_apply_sorted(const uint64_t* __restrict__ pairs, const int* __restrict__ n_val
         if (is_long) continue;
         RowIO<LPR>::template finish<MODE>(row, acc, sub, w, m, v, W, M, V, dense, opt);
     }
-    // rows with many contributions (listed by k_bucket_sort): the whole CTA reduces one row -- contribution t goes to
-    // group t % GPC, partials are combined in group order -> deterministic.  Normally the list is empty.
-    const int n_long = min(*n_long_ptr, long_cap);
-    for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
-        const uint2 e = longs[q];
-        const int j0 = (int)e.x, len = (int)e.y;
-        const int64_t row = (int64_t)(pairs[j0] >> 32);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = grp; t < len; t += GPC) {
-            const float* base;
-            int ld;
-            int64_t r;
-            float c;
-            b_contribution(s0, s1, (uint32_t)pairs[j0 + t], base, ld, r, c);
-            fma4(acc, c, ld4(base + r * ld + sub * 4));
-        }
-        part[grp][sub] = acc;
-        __syncthreads();
-        if (grp == 0) {
-            float4 tot = part[0][sub];
-            for (int g2 = 1; g2 < GPC; ++g2) {
-                const float4 y = part[g2][sub];
-                tot.x += y.x; tot.y += y.y; tot.z += y.z; tot.w += y.w;
-            }
-            float4 w, m, v;
-            if (MODE == 2) {
-                w = ld4(W + row * D + sub * 4);
-                if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-            } else {
-                w = ld4(dense + row * D + sub * 4);
-            }
-            RowIO<LPR>::template finish<MODE>(row, tot, sub, w, m, v, W, M, V, dense, opt);
-        }
-        __syncthreads();
-    }
+    apply_long_rows<LPR, MODE>(pairs, n_long_ptr, longs, long_cap, s0, s1, W, M, V, dense, opt, part);
 }
 
 struct BucketGeom {
@@ -519,12 +635,41 @@ extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d
         k_apply_sorted<LPR, MODE><<<(int)(need < cap ? need : cap), kBT, 0, s>>>(pairs, n_valid, n_long, longs, L.long_cap, \
                                                                                 a, b, W, m, v, dense, ok);       \
     } while (0)
-    if (mode == 1) {
+    static const int pipe_s = [] { const char* e = getenv("B2R_APPLY_PIPE"); return e ? atoi(e) : 0; }();
+    static const int pipe_ctas = [] { const char* e = getenv("B2R_APPLY_CTAS"); return e ? atoi(e) : 0; }();
+#define B2R_PIPE(LPR, S)                                                                                           \
+    do {                                                                                                           \
+        constexpr int GPC = kBT / LPR;                                                                             \
+        const size_t smem = (size_t)S * kBT * (3 * 16 + 8);                                                        \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            B2R_CUDA_OK(cudaFuncSetAttribute(k_apply_sorted_pipe<LPR, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                          \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        int per_sm = (int)((200 * 1024) / (smem + 4096 + 1024));                                                   \
+        if (per_sm > 8) per_sm = 8;                                                                                \
+        if (pipe_ctas > 0) per_sm = pipe_ctas;                                                                     \
+        int64_t need = (n + GPC - 1) / GPC;                                                                        \
+        const int64_t cap = (int64_t)sm_count() * per_sm;                                                          \
+        k_apply_sorted_pipe<LPR, S><<<(int)(need < cap ? need : cap), kBT, smem, s>>>(                             \
+            pairs, n_valid, n_long, longs, L.long_cap, a, b, W, m, v, ok);                                         \
+    } while (0)
+#define B2R_PIPE_D(S)                                                                                              \
+    do {                                                                                                           \
+        if (d == 32) B2R_PIPE(8, S); else if (d == 64) B2R_PIPE(16, S); else B2R_PIPE(32, S);                      \
+    } while (0)
+    if (mode == 2 && pipe_s >= 2) {
+        if (pipe_s == 2) B2R_PIPE_D(2); else if (pipe_s == 3) B2R_PIPE_D(3); else if (pipe_s == 4) B2R_PIPE_D(4);
+        else if (pipe_s <= 6) B2R_PIPE_D(6); else B2R_PIPE_D(8);
+    } else if (mode == 1) {
         if (d == 32) B2R_BK(8, 1); else if (d == 64) B2R_BK(16, 1); else B2R_BK(32, 1);
     } else {
         if (d == 32) B2R_BK(8, 2); else if (d == 64) B2R_BK(16, 2); else B2R_BK(32, 2);
     }
 #undef B2R_BK
+#undef B2R_PIPE
+#undef B2R_PIPE_D
     B2R_LAUNCH_OK("k_apply_sorted");
     return 0;
 }

@@ -150,6 +150,73 @@ def pair_runs_sum(out: torch.Tensor, key: torch.Tensor, rows: torch.Tensor, coef
                                    T.shape[1], _stream()), "b2r_pair_runs_sum")
 
 
+def gt_rank(pred: torch.Tensor) -> torch.Tensor:
+    """rank[r] = #{c : pred[r, c] >= pred[r, 0]} as int64 on the device (helpers/BaseRunner.py:63)."""
+    _need_cuda(pred)
+    pred = _f32c(pred, "pred")
+    if pred.dim() != 2 or pred.shape[1] < 1:
+        raise ValueError("pred must be [N, C] with C >= 1")
+    N, Cn = pred.shape
+    rank = torch.empty(N, dtype=torch.int64, device=pred.device)
+    _lib.check(_lib.load().b2r_gt_rank(_p(pred), N, Cn, Cn, _p(rank), _stream()), "b2r_gt_rank")
+    return rank
+
+
+def rank_histogram(rank: torch.Tensor, kmax: int) -> torch.Tensor:
+    """hist[k] = #{rank == k} for k <= kmax, hist[kmax + 1] = #{rank > kmax}; int64 [kmax + 2] on the device."""
+    _need_cuda(rank)
+    rank = _i64c(rank.reshape(-1), "rank")
+    hist = torch.empty(kmax + 2, dtype=torch.int64, device=rank.device)
+    _lib.check(_lib.load().b2r_rank_histogram(_p(rank), rank.numel(), int(kmax), _p(hist), _stream()),
+               "b2r_rank_histogram")
+    return hist
+
+
+def metrics_from_histogram(hist, n_rows: int, topk, metrics) -> dict:
+    """HR@k / NDCG@k of helpers/BaseRunner.py:64-76 from the rank histogram: every row of rank r <= k contributes
+    1 (HR) or 1/log2(r+1) (NDCG); the mean is over all n_rows rows."""
+    import numpy as np
+    h = np.asarray(hist.cpu() if isinstance(hist, torch.Tensor) else hist, dtype=np.int64)
+    out = {}
+    for k in topk:
+        r = np.arange(1, int(k) + 1)
+        cnt = h[1:int(k) + 1].astype(np.float64)
+        for metric in metrics:
+            key = f"{metric}@{k}"
+            if metric == "HR":
+                out[key] = cnt.sum() / n_rows
+            elif metric == "NDCG":
+                out[key] = (cnt / np.log2(r + 1)).sum() / n_rows
+            else:
+                raise ValueError(f"Undefined evaluation metric: {metric}.")
+    return out
+
+
+def rank_all_items(q: torch.Tensor, table: torch.Tensor, target: torch.Tensor,
+                   mask_row: Optional[torch.Tensor] = None, mask_item: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Ranks under the test_all protocol (BaseModel.py:194-198 + BaseRunner.py:244-251) without the [B, n_items]
+    score matrix: q [B, d] query rows, table [n_items, d], target [B]; (mask_row, mask_item) unique (batch row,
+    item id) pairs whose scores the reference overwrites with -inf."""
+    _need_cuda(q, table, target, mask_row, mask_item)
+    q, table, target = _f32c(q, "q"), _f32c(table, "table"), _i64c(target.reshape(-1), "target")
+    if q.dim() != 2 or table.dim() != 2 or q.shape[1] != table.shape[1] or target.numel() != q.shape[0]:
+        raise ValueError("rank_all_items: q [B, d], table [n_items, d], target [B]")
+    n_mask = 0
+    if mask_row is not None:
+        mask_row, mask_item = _i64c(mask_row.reshape(-1), "mask_row"), _i64c(mask_item.reshape(-1), "mask_item")
+        if mask_row.numel() != mask_item.numel():
+            raise ValueError("mask_row and mask_item must have the same length")
+        n_mask = mask_row.numel()
+    B, d = q.shape
+    rank = torch.empty(B, dtype=torch.int64, device=q.device)
+    s0 = torch.empty(B, dtype=torch.float32, device=q.device)
+    _lib.check(_lib.load().b2r_rank_all_items(_p(q), d, _p(table), _p(target), B, table.shape[0], d,
+                                              _p(mask_row) if n_mask else None, _p(mask_item) if n_mask else None,
+                                              n_mask, _p(s0), _p(rank), _p(err_flag(q.device)), _stream()),
+               "b2r_rank_all_items")
+    return rank
+
+
 def bpr_loss_and_grad(pred: torch.Tensor, want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """BaseModel.py:175-189 value and closed-form d loss / d pred in one pass."""
     _need_cuda(pred)

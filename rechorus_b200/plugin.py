@@ -79,6 +79,28 @@ class _KernelModelMixin:
         with torch.no_grad():
             return self.forward(feed_dict)
 
+    # Evaluation on the device.  Models whose candidate score is a dot product with an item-table
+    # row return (query rows [B, d], item table) here; others return None and are ranked from their predictions.
+    def query_rows(self, feed_dict: dict):
+        return None
+
+    def eval_ranks(self, feed_dict: dict, mask_row=None, mask_item=None) -> torch.Tensor:
+        """int64 [B] ranks of the ground-truth item (helpers/BaseRunner.py:63) for one evaluation batch, computed
+        on the device.  Under the test_all protocol (candidates = [target] + arange(1, n_items),
+        BaseModel.py:194-198) a dot-product model is ranked without materialising the [B, n_items] scores;
+        (mask_row, mask_item) are the (batch row, item id) pairs BaseRunner.py:244-251 would set to -inf."""
+        with torch.no_grad():
+            item_id = feed_dict["item_id"]
+            qr = self.query_rows(feed_dict) if getattr(self, "test_all", 0) else None
+            if qr is not None and item_id.shape[1] == self.item_num:
+                q, table = qr
+                return ops.rank_all_items(q, table, item_id[:, 0], mask_row, mask_item)
+            pred = self.forward(feed_dict)["prediction"]
+            if mask_row is not None and mask_row.numel() > 0:
+                pred = pred.clone()
+                pred[mask_row, mask_item] = float("-inf")
+            return ops.gt_rank(pred)
+
 
 class BPRMFKernels(_KernelModelMixin):
     """models/general/BPRMF.py:18-45 (BPRMFBase) on K1/K2."""
@@ -112,6 +134,10 @@ class BPRMFKernels(_KernelModelMixin):
         u = ops.embedding(self.u_embeddings.weight, u_ids)            # [B, d]   (gather kernel)
         pred = ops.score(u, self.i_embeddings.weight, i_ids)          # [B, C]   (gather + dot kernel)
         return {"prediction": pred.view(feed_dict["batch_size"], -1)}
+
+    def query_rows(self, feed_dict):
+        with torch.no_grad():
+            return ops.embedding(self.u_embeddings.weight, feed_dict["user_id"]), self.i_embeddings.weight
 
     def train_step(self, feed_dict, next_feed_dict=None) -> torch.Tensor:
         """One whole training step (forward, BPR loss, backward, row-sparse optimizer update) enqueued by a
@@ -264,6 +290,10 @@ class SASRecKernels(_KernelModelMixin):
                 o = torch.nn.functional.dropout(o, p, self.training)
             x = ops.add_layernorm(o, c, blk.layer_norm2.weight, blk.layer_norm2.bias)
         return ops.select_last(x, history, lengths)                                                    # [B, d]
+
+    def query_rows(self, feed_dict):
+        with torch.no_grad():
+            return self.user_state(feed_dict["history_items"], feed_dict["lengths"]), self.i_embeddings.weight
 
     def forward(self, feed_dict):
         self.check_list = []

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
+from . import ops
 from .optim import RowSparseOptimizer
 
 
@@ -57,6 +58,9 @@ class BaseRunner:
         parser.add_argument("--main_metric", type=str, default="", help="Metric that selects the best model.")
         parser.add_argument("--fused_optimizer", type=int, default=0,
                             help="1: row-sparse fused SGD/Adam/Adagrad (rechorus_b200.optim) instead of torch.optim")
+        parser.add_argument("--device_metrics", type=int, default=0,
+                            help="1: rank the ground truth on the GPU (model.eval_ranks) instead of copying predictions "
+                                 "to the host for evaluate_method")
         return parser
 
     @staticmethod
@@ -91,6 +95,7 @@ class BaseRunner:
         self.num_workers = args.num_workers
         self.pin_memory = args.pin_memory
         self.fused_optimizer = getattr(args, "fused_optimizer", 0)
+        self.device_metrics = getattr(args, "device_metrics", 0)
         self.topk = [int(x) for x in args.topk.split(",")]
         self.metrics = [m.strip().upper() for m in args.metric.split(",")]
         self.main_metric = args.main_metric or f"{self.metrics[0]}@{self.topk[0]}"
@@ -190,7 +195,39 @@ class BaseRunner:
         return len(criterion) - criterion.index(max(criterion)) > self.early_stop
 
     def evaluate(self, dataset, topks: list, metrics: list) -> Dict[str, float]:
+        if self.device_metrics and hasattr(dataset.model, "eval_ranks"):
+            return self.evaluate_on_device(dataset, topks, metrics)
         return self.evaluate_method(self.predict(dataset), topks, metrics)
+
+    def evaluate_on_device(self, dataset, topks: list, metrics: list) -> Dict[str, float]:
+        """helpers/BaseRunner.py:216-252 with the predictions never leaving the GPU: per batch the model returns
+        the integer ranks of the ground truth (``eval_ranks``), a rank histogram is accumulated on the device and
+        HR@k / NDCG@k are read off it -- (max k + 2) integers cross PCIe per evaluation instead of N x C floats."""
+        model = dataset.model
+        model.eval()
+        kmax = max(int(k) for k in topks)
+        hist, n_rows = None, 0
+        dl = DataLoader(dataset, batch_size=self.eval_batch_size, shuffle=False, num_workers=self.num_workers,
+                        collate_fn=dataset.collate_batch, pin_memory=bool(self.pin_memory))
+        start = 0
+        for batch in dl:
+            bs = batch["batch_size"]
+            mask_row = mask_item = None
+            if model.test_all:
+                rows, cols = [], []
+                for i, u in enumerate(dataset.data["user_id"][start:start + bs]):
+                    clicked = list(dataset.corpus.train_clicked_set[u] | dataset.corpus.residual_clicked_set[u])
+                    rows.extend([i] * len(clicked))
+                    cols.extend(clicked)
+                mask_row = torch.tensor(rows, dtype=torch.int64, device=model.device)
+                mask_item = torch.tensor(cols, dtype=torch.int64, device=model.device)
+            batch = batch_to_device(batch, model.device)
+            ranks = model.eval_ranks(batch, mask_row, mask_item)
+            h = ops.rank_histogram(ranks, kmax)
+            hist = h if hist is None else hist + h
+            n_rows += bs
+            start += bs
+        return ops.metrics_from_histogram(hist, n_rows, topks, metrics)
 
     def predict(self, dataset, save_prediction: bool = False) -> np.ndarray:
         """helpers/BaseRunner.py:225-252 (uses the model's no-grad ``inference`` hook when present)."""

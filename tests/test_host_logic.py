@@ -97,3 +97,24 @@ def test_eval_termination_rule():
     assert not r.eval_termination([0.1, 0.2, 0.3])
     assert r.eval_termination([0.5, 0.4, 0.3, 0.2])            # non-increasing tail
     assert r.eval_termination([0.9, 0.1, 0.2, 0.3, 0.4])       # best is more than early_stop epochs ago
+
+
+def test_metrics_from_histogram_equal_evaluate_method():
+    """HR@k / NDCG@k read off a rank histogram equal helpers/BaseRunner.py:52-78 applied to the predictions."""
+    import numpy as np
+    from oracle import rechorus_oracle as O
+    from rechorus_b200 import ops
+    rng = np.random.RandomState(0)
+    pred = rng.randn(999, 60).astype(np.float32)
+    pred[:, 0] += 1.0
+    rank = O.gt_rank(pred)
+    kmax = 20
+    hist = np.bincount(np.minimum(rank, kmax + 1), minlength=kmax + 2)
+    ours = ops.metrics_from_histogram(hist, len(rank), [1, 5, 20], ["HR", "NDCG"])
+    ref = O.rank_metrics(pred, [1, 5, 20], ["HR", "NDCG"])
+    assert set(ours) == set(ref)
+    for k in ref:
+        assert abs(ours[k] - ref[k]) <= 1e-12
+    import pytest
+    with pytest.raises(ValueError):
+        ops.metrics_from_histogram(hist, len(rank), [5], ["MRR"])

@@ -1,4 +1,4 @@
-"""CPU, world_size 2 over gloo: the exchange bookkeeping of rechorus_b200.shard.ShardedBPRMF (bucketing by owner,
+"""CPU, world_size 2 and 4 over gloo: the exchange bookkeeping of rechorus_b200.shard.ShardedBPRMF (bucketing by owner,
 fixed-capacity buffers, all-to-all / all-gather / reduce-scatter wiring, un-permutation) with a torch stand-in for
 the local kernels, checked against a single-process oracle of the same global step.  The stand-in lives here, in the
 tests: the product backend (CudaBackend) has no CPU path."""
@@ -79,8 +79,9 @@ def _worker(rank, world, port, out_q):
     m = ShardedBPRMF(N_USERS, N_ITEMS, D, torch.device("cpu"), backend=CpuStandIn(), optimizer="SGD", lr=LR,
                      cap_factor=3.0)
     U, I = _global_tables()
-    m.U.copy_(U[rank * m.rows_u:(rank + 1) * m.rows_u])
-    m.I.copy_(I[rank * m.rows_i:(rank + 1) * m.rows_i])
+    pad = lambda T, rows: torch.cat([T, torch.zeros(rows * world - T.shape[0], D)])   # last shard may be ragged
+    m.U.copy_(pad(U, m.rows_u)[rank * m.rows_u:(rank + 1) * m.rows_u])
+    m.I.copy_(pad(I, m.rows_i)[rank * m.rows_i:(rank + 1) * m.rows_i])
     losses = []
     for uid, iid in _batches(rank):
         pred, _ = m.scores(uid, iid)
@@ -90,8 +91,8 @@ def _worker(rank, world, port, out_q):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_step_equals_single_process_oracle():
-    world = 2
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_step_equals_single_process_oracle(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

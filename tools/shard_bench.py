@@ -54,23 +54,32 @@ def main():
             U, I = m.U, m.I
         ref = torch.einsum("bd,bcd->bc", U[uid], I[iid])
         err = float((pred - ref).abs().max())
-        Ib = I.clone()
-        loss = m.train_step(uid, iid)
-        # item-shard update check (SGD-free: just that touched rows moved and untouched did not, on this rank's shard)
-        lo = rank * m.rows_i
-        moved = (m.I != Ib[lo:lo + m.rows_i]).any(1)
-        all_ids = iid.reshape(-1)
+        # exact expected SGD step of the global objective (mean over the W*B samples) from the gathered tables
         if world > 1:
-            allg = torch.empty(world * all_ids.numel(), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(allg, all_ids)
+            uid_all = torch.empty(world * uid.numel(), dtype=torch.int64, device=dev)
+            iid_all = torch.empty(world * iid.numel(), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(uid_all, uid)
+            dist.all_gather_into_tensor(iid_all, iid.reshape(-1))
+            iid_all = iid_all.view(-1, C)
         else:
-            allg = all_ids
-        touched = torch.zeros(m.rows_i, dtype=torch.bool, device=dev)
-        mine = allg[(allg >= lo) & (allg < lo + m.rows_i)] - lo
-        touched[mine] = True
-        ok = bool(torch.equal(moved, touched))
+            uid_all, iid_all = uid, iid
+        Ug, Ig = U.clone().requires_grad_(True), I.clone().requires_grad_(True)
+        p_all = torch.einsum("bd,bcd->bc", Ug[uid_all], Ig[iid_all])
+        pos, neg = p_all[:, :1], p_all[:, 1:]
+        wgt = torch.softmax(neg - neg.max(), dim=1)
+        total = -torch.log(((pos - neg).sigmoid() * wgt).sum(1).clamp(1e-8, 1 - 1e-8)).mean()
+        gU, gI = torch.autograd.grad(total, [Ug, Ig])
+        loss = m.train_step(uid, iid)
+        lo_i, lo_u = rank * m.rows_i, rank * m.rows_u
+        exp_I = (I - 1e-3 * gI)[lo_i:lo_i + m.rows_i]
+        exp_U = (U - 1e-3 * gU)[lo_u:lo_u + m.rows_u]
+        upd_err = max(float((m.I - exp_I).abs().max()), float((m.U - exp_U).abs().max()))
+        # relative to the size of the update itself (lr * |g| is tiny at init): the step must be reproduced, not lost
+        upd_rel = float(((m.I - I[lo_i:lo_i + m.rows_i]) - (exp_I - I[lo_i:lo_i + m.rows_i])).abs().max()
+                        / (1e-3 * gI.abs().max()).clamp_min(1e-30))
+        ok = upd_err <= 1e-6 and upd_rel <= 1e-3
         ops.check_ids(dev)
-        print(json.dumps({"rank": rank, "check_max_abs_err": err, "touched_rows_match": ok, "loss": float(loss)}), flush=True)
+        print(json.dumps({"rank": rank, "check_max_abs_err": err, "update_max_abs_err": upd_err, "update_rel_err": upd_rel, "update_ok": ok, "loss": float(loss)}), flush=True)
         assert err <= 1e-5 and ok
     for k in range(a.warmup):
         m.train_step(*pool[k % 4])
