@@ -134,6 +134,7 @@ k_bucket_scan(int* __restrict__ count, int* __restrict__ cursor, int* __restrict
         off[nb] = carry;
         off[nb + 1] = nbig;          // number of buckets too large for the shared-memory sort (informational)
         off[nb + 2] = 0;             // long-row counter, filled by k_bucket_sort
+        off[nb + 3] = 0;             // row-head counter, filled by k_bucket_sort
     }
 }
 
@@ -199,6 +200,45 @@ __device__ __forceinline__ int lower_bound64(const uint64_t* a, int n, uint64_t 
     return lo;
 }
 
+// After a bucket is sorted (a = its pairs, in shared or global memory): list every row's first pair as
+// (row, position of the first pair, index of the first pair, run length) for k_apply_sorted, which then never has to
+// discover run boundaries itself.  Rows with >= kLong contributions go to the cooperative list instead (their head
+// entry carries length 0).  Slots are reserved with one global atomic per bucket; the order of the list does not
+// influence any result (each row is reduced by exactly one lane group, in ascending position).
+__device__ __forceinline__ void emit_row_heads(const uint64_t* a, int cnt, int beg, int* n_long, uint2* longs,
+                                               int long_cap, int* n_heads, uint4* heads, int* head_cnt,
+                                               int* head_base) {
+    __syncthreads();                                   // a[] complete, *head_cnt == 0
+    int mine = 0;
+    for (int i = threadIdx.x; i < cnt; i += kBT)
+        mine += (i == 0 || (uint32_t)(a[i - 1] >> 32) != (uint32_t)(a[i] >> 32)) ? 1 : 0;
+    if (mine) atomicAdd(head_cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *head_base = atomicAdd(n_heads, *head_cnt);
+        *head_cnt = 0;
+    }
+    __syncthreads();
+    const int base = *head_base;
+    for (int i = threadIdx.x; i < cnt; i += kBT) {
+        const uint64_t v = a[i];
+        const uint32_t key = (uint32_t)(v >> 32);
+        if (i == 0 || (uint32_t)(a[i - 1] >> 32) != key) {
+            const int len = lower_bound64(a, cnt, ((uint64_t)key + 1) << 32) - i;
+            const bool is_long = len >= kLong;
+            if (is_long) {
+                const int q = atomicAdd(n_long, 1);
+                if (q < long_cap) longs[q] = make_uint2((uint32_t)(beg + i), (uint32_t)len);
+            }
+            const int slot = base + atomicAdd(head_cnt, 1);
+            heads[slot] = make_uint4(key, (uint32_t)v, (uint32_t)(beg + i), is_long ? 0u : (uint32_t)len);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *head_cnt = 0;
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // k_bucket_sort: one CTA per bucket sorts its (row, position) pairs in place.  Buckets cover ascending, disjoint
 // row ranges, so afterwards the whole pairs array is sorted by (row, position) -- the same order a device-wide
@@ -208,9 +248,13 @@ __device__ __forceinline__ int lower_bound64(const uint64_t* a, int n, uint64_t 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBT)
 k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const int* __restrict__ off, int nb,
-              int* __restrict__ n_long, uint2* __restrict__ longs, int long_cap) {
+              int* __restrict__ n_long, uint2* __restrict__ longs, int long_cap, int* __restrict__ n_heads,
+              uint4* __restrict__ heads) {
     __shared__ uint64_t s[kCap];
+    __shared__ int head_cnt, head_base;
     const int tid = threadIdx.x;
+    if (tid == 0) head_cnt = 0;
+    __syncthreads();
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
         const int beg = off[b];
         const int cnt = off[b + 1] - beg;
@@ -222,19 +266,8 @@ k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const in
             for (int i = tid; i < P; i += kBT) s[i] = i < cnt ? g[i] : ~0ull;
             __syncthreads();
             bitonic_sort_smem(s, P);
-            for (int i = tid; i < cnt; i += kBT) {
-                const uint64_t v = s[i];
-                g[i] = v;
-                const uint32_t key = (uint32_t)(v >> 32);
-                if (i == 0 || (uint32_t)(s[i - 1] >> 32) != key) {          // run head: length by binary search
-                    const int ub = lower_bound64(s, cnt, ((uint64_t)key + 1) << 32);
-                    if (ub - i >= kLong) {
-                        const int q = atomicAdd(n_long, 1);
-                        if (q < long_cap) longs[q] = make_uint2((uint32_t)(beg + i), (uint32_t)(ub - i));
-                    }
-                }
-            }
-            __syncthreads();
+            for (int i = tid; i < cnt; i += kBT) g[i] = s[i];
+            emit_row_heads(s, cnt, beg, n_long, longs, long_cap, n_heads, heads, &head_cnt, &head_base);
         } else {
             // chunked shared-memory sorts ...
             for (int c0 = 0; c0 < cnt; c0 += kCap) {
@@ -268,17 +301,7 @@ k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const in
                 for (int i = tid; i < cnt; i += kBT) g[i] = src[i];
                 __syncthreads();
             }
-            for (int i = tid; i < cnt; i += kBT) {
-                const uint32_t key = (uint32_t)(g[i] >> 32);
-                if (i == 0 || (uint32_t)(g[i - 1] >> 32) != key) {
-                    const int ub = lower_bound64(g, cnt, ((uint64_t)key + 1) << 32);
-                    if (ub - i >= kLong) {
-                        const int q = atomicAdd(n_long, 1);
-                        if (q < long_cap) longs[q] = make_uint2((uint32_t)(beg + i), (uint32_t)(ub - i));
-                    }
-                }
-            }
-            __syncthreads();
+            emit_row_heads(g, cnt, beg, n_long, longs, long_cap, n_heads, heads, &head_cnt, &head_base);
         }
     }
 }
@@ -330,130 +353,26 @@ __device__ __forceinline__ void apply_long_rows(const uint64_t* __restrict__ pai
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_apply_sorted_pipe: the same walk with the weight/state rows of a lane group's next S-1 pairs already in flight.
-// The rows are fetched with cp.async (16 B per lane, L1 bypassed) into a per-group ring in shared memory, so the bytes
-// in flight per SM are bounded by shared memory (S * 768 B per group at d=64 with Adam) instead of by the registers
-// that hold load results; the keys of the pair after those are fetched one iteration earlier still.  Every lane
-// reads back only what it copied itself, so cp.async.wait_group is the only synchronisation.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem, const void* gptr) {
-    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-template <int LPR, int S>
-__global__ void __launch_bounds__(kBT)
-k_apply_sorted_pipe(const uint64_t* __restrict__ pairs, const int* __restrict__ n_valid_ptr,
-                    const int* __restrict__ n_long_ptr, const uint2* __restrict__ longs, int long_cap, BSrc s0, BSrc s1,
-                    float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, OptK opt) {
-    constexpr int D = LPR * 4;
-    constexpr int GPC = kBT / LPR;
-    constexpr uint64_t kSkip = ~0ull;            // ring entry of a pair that is not the head of its row
-    extern __shared__ __align__(16) unsigned char pipe_smem[];
-    float4* rows = reinterpret_cast<float4*>(pipe_smem);                       // [S][3][kBT]
-    uint64_t* ring = reinterpret_cast<uint64_t*>(rows + S * 3 * kBT);          // [S][kBT]
-    __shared__ float4 part[GPC][LPR];
-    const int tid = threadIdx.x, sub = tid % LPR, grp = tid / LPR;
-    const int n_valid = *n_valid_ptr;
-    const int stride = gridDim.x * GPC;
-    const int j0 = blockIdx.x * GPC + grp;
-    const int first = blockIdx.x * GPC;
-    const int iters = first < n_valid ? (n_valid - first + stride - 1) / stride : 0;
-    const int sld = opt.state_ld ? opt.state_ld : D;
-
-    uint64_t kc = kSkip;
-    uint32_t kp = 0;
-    auto fetch_keys = [&](int it) {
-        const int j = j0 + it * stride;
-        if (it < iters && j < n_valid) {
-            kc = pairs[j];
-            kp = j > 0 ? (uint32_t)(pairs[j - 1] >> 32) : ~(uint32_t)(kc >> 32);
-        } else {
-            kc = kSkip;
-            kp = 0xffffffffu;
-        }
-    };
-    auto issue = [&](int it) {
-        const int slot = it % S;
-        const uint32_t key = (uint32_t)(kc >> 32);
-        const bool head = key != kp;
-        ring[slot * kBT + tid] = head ? kc : kSkip;
-        if (head) {
-            const int64_t row = (int64_t)key;
-            cp_async16(&rows[(slot * 3 + 0) * kBT + tid], W + row * D + sub * 4);
-            if (opt.kind == 1) cp_async16(&rows[(slot * 3 + 1) * kBT + tid], M + row * sld + sub * 4);
-            if (opt.kind != 0) cp_async16(&rows[(slot * 3 + 2) * kBT + tid], V + row * sld + sub * 4);
-        }
-        cp_async_commit();
-    };
-    for (int it = 0; it < S - 1; ++it) {
-        fetch_keys(it);
-        issue(it);
-    }
-    fetch_keys(S - 1);
-    for (int i = 0; i < iters; ++i) {
-        issue(i + S - 1);
-        fetch_keys(i + S);
-        cp_async_wait<S - 1>();
-        const int slot = i % S;
-        uint64_t cur = ring[slot * kBT + tid];
-        if (cur == kSkip) continue;
-        const uint32_t key = (uint32_t)(cur >> 32);
-        const int64_t row = (int64_t)key;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int len = 0;
-        bool is_long = false;
-        for (int jj = j0 + i * stride;;) {
-            const float* base;
-            int ld;
-            int64_t r;
-            float c;
-            b_contribution(s0, s1, (uint32_t)cur, base, ld, r, c);
-            fma4(acc, c, ld4(base + r * ld + sub * 4));
-            ++len;
-            if (++jj >= n_valid) break;
-            cur = pairs[jj];
-            if ((uint32_t)(cur >> 32) != key) break;
-            if (len >= kLong) {
-                is_long = true;
-                break;
-            }
-        }
-        if (is_long) continue;
-        float4 w = rows[(slot * 3 + 0) * kBT + tid], m, v;
-        if (opt.kind == 1) m = rows[(slot * 3 + 1) * kBT + tid];
-        if (opt.kind != 0) v = rows[(slot * 3 + 2) * kBT + tid];
-        RowIO<LPR>::template finish<2>(row, acc, sub, w, m, v, W, M, V, nullptr, opt);
-    }
-    cp_async_wait<0>();
-    apply_long_rows<LPR, 2>(pairs, n_long_ptr, longs, long_cap, s0, s1, W, M, V, nullptr, opt, part);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_apply_sorted: one lane group per pair index; the group whose pair is the first of its row owns the row: it
-// requests the weight/state rows, walks the row's contributions (ascending position), applies the update.
-// Rows with >= kLong contributions are left to k_apply_long.  No shared memory, no barriers.
+// k_apply_sorted: one lane group per touched row (the head list written by k_bucket_sort): request the weight/state
+// rows, sum the row's contributions in ascending position -- the first one is named by the head entry itself, so a
+// row with a single contribution never reads the pair array -- and apply the update.  No shared memory, no
+// barriers, no atomics.  Rows with >= kLong contributions are reduced afterwards by whole CTAs.
 // ---------------------------------------------------------------------------------------------------
 template <int LPR, int MODE>
 __global__ void __launch_bounds__(kBT)
-k_apply_sorted(const uint64_t* __restrict__ pairs, const int* __restrict__ n_valid_ptr, const int* __restrict__ n_long_ptr,
-               const uint2* __restrict__ longs, int long_cap, BSrc s0, BSrc s1,
+k_apply_sorted(const uint64_t* __restrict__ pairs, const uint4* __restrict__ heads, const int* __restrict__ n_heads_ptr,
+               const int* __restrict__ n_long_ptr, const uint2* __restrict__ longs, int long_cap, BSrc s0, BSrc s1,
                float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense, OptK opt) {
     constexpr int D = LPR * 4;
     constexpr int GPC = kBT / LPR;
     __shared__ float4 part[GPC][LPR];          // only touched when the batch has rows with >= kLong contributions
     const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
-    const int n_valid = *n_valid_ptr;
-    for (int j = blockIdx.x * GPC + grp; j < n_valid; j += gridDim.x * GPC) {
-        uint64_t cur = pairs[j];
-        const uint32_t key = (uint32_t)(cur >> 32);
-        if (j > 0 && (uint32_t)(pairs[j - 1] >> 32) == key) continue;       // not the head of its row
-        const int64_t row = (int64_t)key;
+    const int n_heads = *n_heads_ptr;
+    for (int h = blockIdx.x * GPC + grp; h < n_heads; h += gridDim.x * GPC) {
+        const uint4 e = __ldg(heads + h);
+        const int len = (int)e.w;
+        if (len == 0) continue;                // long row: handled below
+        const int64_t row = (int64_t)e.x;
         float4 w, m, v;
         if (MODE == 2) {
             w = ld4(W + row * D + sub * 4);
@@ -463,25 +382,17 @@ k_apply_sorted(const uint64_t* __restrict__ pairs, const int* __restrict__ n_val
             w = ld4(dense + row * D + sub * 4);
         }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int len = 0;
-        bool is_long = false;
-        for (int jj = j;;) {
+        uint32_t pos = e.y;
+        for (int t = 0;;) {
             const float* base;
             int ld;
             int64_t r;
             float c;
-            b_contribution(s0, s1, (uint32_t)cur, base, ld, r, c);
+            b_contribution(s0, s1, pos, base, ld, r, c);
             fma4(acc, c, ld4(base + r * ld + sub * 4));
-            ++len;
-            if (++jj >= n_valid) break;
-            cur = pairs[jj];
-            if ((uint32_t)(cur >> 32) != key) break;
-            if (len >= kLong) {
-                is_long = true;
-                break;
-            }
+            if (++t >= len) break;
+            pos = (uint32_t)pairs[e.z + t];
         }
-        if (is_long) continue;
         RowIO<LPR>::template finish<MODE>(row, acc, sub, w, m, v, W, M, V, dense, opt);
     }
     apply_long_rows<LPR, MODE>(pairs, n_long_ptr, longs, long_cap, s0, s1, W, M, V, dense, opt, part);
@@ -506,7 +417,7 @@ static BucketGeom bucket_geom(int64_t n, int64_t n_rows) {
 }
 
 struct BucketLayout {
-    size_t count, cursor, off, pairs, tmp, longs, total;
+    size_t count, cursor, off, pairs, tmp, longs, heads, total;
     int long_cap;
 };
 
@@ -521,11 +432,12 @@ static BucketLayout bucket_layout(int64_t n, int64_t n_rows) {
     };
     L.count = take((size_t)g.nb * 4 * kPad);
     L.cursor = take((size_t)g.nb * 4 * kPad);
-    L.off = take((size_t)(g.nb + 3) * 4);
+    L.off = take((size_t)(g.nb + 4) * 4);
     L.pairs = take((size_t)n * 8);
     L.tmp = take((size_t)n * 8);
     L.long_cap = (int)(n / kLong + 1);
     L.longs = take((size_t)L.long_cap * 8);
+    L.heads = take((size_t)n * 16);
     L.total = o;
     return L;
 }
@@ -592,7 +504,9 @@ extern "C" int b2r_bucket_partition(const int64_t* ids, int64_t n, int64_t n_row
     const int sort_cap = sm_count() * 8;
     k_bucket_sort<<<g.nb < sort_cap ? g.nb : sort_cap, kBT, 0, s>>>(pairs, reinterpret_cast<uint64_t*>(base + L.tmp), off,
                                                                    g.nb, off + g.nb + 2,
-                                                                   reinterpret_cast<uint2*>(base + L.longs), L.long_cap);
+                                                                   reinterpret_cast<uint2*>(base + L.longs), L.long_cap,
+                                                                   off + g.nb + 3,
+                                                                   reinterpret_cast<uint4*>(base + L.heads));
     B2R_LAUNCH_OK("k_bucket_sort");
     return 0;
 }
@@ -625,51 +539,23 @@ extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d
     const BSrc a = to_bsrc(s0, d), b = to_bsrc(s1, d);
     const OptK ok = make_optk(o);
     const uint2* longs = reinterpret_cast<const uint2*>(base + L.longs);
-    const int* n_valid = off + g.nb;                 // total number of (non-ignored) pairs, written by the scan
+    const int* n_heads = off + g.nb + 3;             // touched rows, listed by k_bucket_sort
+    const uint4* heads = reinterpret_cast<const uint4*>(base + L.heads);
     const int* n_long = off + g.nb + 2;
 #define B2R_BK(LPR, MODE)                                                                              \
     do {                                                                                               \
         constexpr int GPC = kBT / LPR;                                                                 \
         int64_t need = (n + GPC - 1) / GPC;                                                            \
         const int64_t cap = (int64_t)sm_count() * 16;                                                  \
-        k_apply_sorted<LPR, MODE><<<(int)(need < cap ? need : cap), kBT, 0, s>>>(pairs, n_valid, n_long, longs, L.long_cap, \
+        k_apply_sorted<LPR, MODE><<<(int)(need < cap ? need : cap), kBT, 0, s>>>(pairs, heads, n_heads, n_long, longs, L.long_cap, \
                                                                                 a, b, W, m, v, dense, ok);       \
     } while (0)
-    static const int pipe_s = [] { const char* e = getenv("B2R_APPLY_PIPE"); return e ? atoi(e) : 0; }();
-    static const int pipe_ctas = [] { const char* e = getenv("B2R_APPLY_CTAS"); return e ? atoi(e) : 0; }();
-#define B2R_PIPE(LPR, S)                                                                                           \
-    do {                                                                                                           \
-        constexpr int GPC = kBT / LPR;                                                                             \
-        const size_t smem = (size_t)S * kBT * (3 * 16 + 8);                                                        \
-        static bool attr_done = false;                                                                             \
-        if (!attr_done) {                                                                                          \
-            B2R_CUDA_OK(cudaFuncSetAttribute(k_apply_sorted_pipe<LPR, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem));                                                          \
-            attr_done = true;                                                                                      \
-        }                                                                                                          \
-        int per_sm = (int)((200 * 1024) / (smem + 4096 + 1024));                                                   \
-        if (per_sm > 8) per_sm = 8;                                                                                \
-        if (pipe_ctas > 0) per_sm = pipe_ctas;                                                                     \
-        int64_t need = (n + GPC - 1) / GPC;                                                                        \
-        const int64_t cap = (int64_t)sm_count() * per_sm;                                                          \
-        k_apply_sorted_pipe<LPR, S><<<(int)(need < cap ? need : cap), kBT, smem, s>>>(                             \
-            pairs, n_valid, n_long, longs, L.long_cap, a, b, W, m, v, ok);                                         \
-    } while (0)
-#define B2R_PIPE_D(S)                                                                                              \
-    do {                                                                                                           \
-        if (d == 32) B2R_PIPE(8, S); else if (d == 64) B2R_PIPE(16, S); else B2R_PIPE(32, S);                      \
-    } while (0)
-    if (mode == 2 && pipe_s >= 2) {
-        if (pipe_s == 2) B2R_PIPE_D(2); else if (pipe_s == 3) B2R_PIPE_D(3); else if (pipe_s == 4) B2R_PIPE_D(4);
-        else if (pipe_s <= 6) B2R_PIPE_D(6); else B2R_PIPE_D(8);
-    } else if (mode == 1) {
+    if (mode == 1) {
         if (d == 32) B2R_BK(8, 1); else if (d == 64) B2R_BK(16, 1); else B2R_BK(32, 1);
     } else {
         if (d == 32) B2R_BK(8, 2); else if (d == 64) B2R_BK(16, 2); else B2R_BK(32, 2);
     }
 #undef B2R_BK
-#undef B2R_PIPE
-#undef B2R_PIPE_D
     B2R_LAUNCH_OK("k_apply_sorted");
     return 0;
 }
