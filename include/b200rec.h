@@ -177,6 +177,24 @@ B2R_API int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d, c
                      const b2r_grad_source* s1, int mode, float* dense, float* W, float* m, float* v,
                      const b2r_optim* opt, b2r_stream_t stream);
 
+/* One table's share of an apply launch (same meaning as the b2r_bucket_apply arguments of those names). */
+typedef struct b2r_apply_job {
+    const void* ws;              /* the table's plan: workspace filled by b2r_bucket_partition */
+    int64_t n, n_rows;
+    const b2r_grad_source* s0;
+    const b2r_grad_source* s1;   /* optional second contribution stream (NULL: none) */
+    float* dense;                /* mode 1 */
+    float* W;                    /* mode 2 */
+    float* m;
+    float* v;
+} b2r_apply_job;
+
+/* b2r_bucket_apply for two tables in ONE launch (job b may be NULL): the two updates must be independent -- neither
+ * job's sources may alias the other job's W -- e.g. the user and the item table of one BPRMF step, the item gradient
+ * reading a saved copy of the user rows.  The small table's update then runs underneath the large one's. */
+B2R_API int b2r_bucket_apply_pair(const b2r_apply_job* a, const b2r_apply_job* b, int d, int mode, const b2r_optim* opt,
+                                  b2r_stream_t stream);
+
 /* Fast, order-nondeterministic alternative to plan+segment for mode 1 (dense += via red.global.add.v4.f32) */
 B2R_API int b2r_scatter_add_atomic(const int64_t* ids, int64_t n_rows, const b2r_grad_source* s, int d,
                            float* dense, int32_t* err_flag, b2r_stream_t stream);

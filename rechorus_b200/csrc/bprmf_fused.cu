@@ -78,7 +78,7 @@ struct FusedPass {
 
     const float* U; const int64_t* uid; int64_t n_users;
     const float* T; const int64_t* ids; int64_t n_t;
-    float* pred; float* gout; float* row_loss; float* dQ;
+    float* pred; float* gout; float* row_loss; float* dQ; float* qout;
     int B, C, GPS; int32_t* err_flag;
     int sub, grp, SPB, j, slot;
     int c_load;          // candidate whose id this lane loads (row `sub` of the group), valid if sub < RPG
@@ -118,6 +118,7 @@ struct FusedPass {
         const float p = group_sum<LPR>(dot4(q, rp));                 // positive's score, known to every group
         const float x = group_sum_multi<LPR, RPG>(d, sub);           // score of candidate c_mine (copies in RS lanes)
         if (mine_ok && pred != nullptr) pred[b * C + c_mine] = x;
+        if (have && j == 0 && qout != nullptr) st4(qout + b * D + sub * 4, q);   // the sample's user row, for dI
         if (STOP == 1) {
             if (mine_ok) gout[b * C + c_mine] = x;
             return;
@@ -193,15 +194,15 @@ __global__ void __launch_bounds__(256, (RPG <= 4) ? 4 : 3)
 k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int64_t n_users,
               const float* __restrict__ T, const int64_t* __restrict__ ids, int64_t n_t,
               float* __restrict__ pred, float* __restrict__ gout, float* __restrict__ row_loss,
-              float* __restrict__ dQ, int B, int C, int GPS, int32_t* err_flag, float* __restrict__ loss_out,
-              unsigned int* __restrict__ done_counter) {
+              float* __restrict__ dQ, float* __restrict__ qout, int B, int C, int GPS, int32_t* err_flag,
+              float* __restrict__ loss_out, unsigned int* __restrict__ done_counter) {
     static_assert(RPG <= LPR, "ids of a group's rows are loaded one per lane");
     using P = FusedPass<LPR, RPG>;
     __shared__ float4 sstat[2][P::GPC];                   // (max, Z, A, D) per group, alternating by pass parity
     __shared__ float4 part[2][P::GPC][LPR];               // partial dQ per group
     P f;
     f.U = U; f.uid = uid; f.n_users = n_users; f.T = T; f.ids = ids; f.n_t = n_t;
-    f.pred = pred; f.gout = gout; f.row_loss = row_loss; f.dQ = dQ; f.B = B; f.C = C; f.GPS = GPS; f.err_flag = err_flag;
+    f.pred = pred; f.gout = gout; f.row_loss = row_loss; f.dQ = dQ; f.qout = qout; f.B = B; f.C = C; f.GPS = GPS; f.err_flag = err_flag;
     f.sub = threadIdx.x % LPR; f.grp = threadIdx.x / LPR;
     f.SPB = P::GPC / GPS; f.j = f.grp % GPS; f.slot = f.grp / GPS;
     f.c_load = f.j + GPS * f.sub;
@@ -270,29 +271,31 @@ using namespace b2r;
 
 // returns B2R_E_UNSUPPORTED (without touching the error string semantics) when the shape has no fused variant
 static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
-                        int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, int B, int C, int d,
-                        int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream);
+                        int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, float* qout, int B,
+                        int C, int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream);
 
 extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64_t n_users, const float* I,
                                        const int64_t* iid, int64_t n_items, float* pred, float* grad_pred,
                                        float* row_loss, float* dQ, int B, int C, int d, int32_t* err_flag,
                                        b2r_stream_t stream) {
-    return fused_launch(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, d, err_flag, nullptr, nullptr,
-                        stream);
+    return fused_launch(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, nullptr, B, C, d, err_flag, nullptr,
+                        nullptr, stream);
 }
 
 // same, and the mean loss is produced by the kernel itself (done_counter: a zero-initialised device word the kernel
-// leaves zero again); used by the step context
+// leaves zero again) and the gathered user rows are kept (qout [B, d]: the item-side gradient's source, so that the
+// user table may be updated while the item table still is); used by the step context
 int b2r_bprmf_fused_fwd_bwd_loss(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
-                                 int64_t n_items, float* grad_pred, float* row_loss, float* dQ, int B, int C, int d,
-                                 int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream) {
-    return fused_launch(U, uid, n_users, I, iid, n_items, nullptr, grad_pred, row_loss, dQ, B, C, d, err_flag, loss_out,
+                                 int64_t n_items, float* grad_pred, float* row_loss, float* dQ, float* qout, int B, int C,
+                                 int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter,
+                                 b2r_stream_t stream) {
+    return fused_launch(U, uid, n_users, I, iid, n_items, nullptr, grad_pred, row_loss, dQ, qout, B, C, d, err_flag, loss_out,
                         done_counter, stream);
 }
 
 static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
-                        int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, int B, int C, int d,
-                        int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream) {
+                        int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, float* qout, int B,
+                        int C, int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream) {
     B2R_REQUIRE(U && uid && I && iid && grad_pred && row_loss && dQ, B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: null pointer");
     B2R_REQUIRE(B > 0 && C > 0, B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: B=%d C=%d", B, C);
     B2R_REQUIRE(aligned16(U) && aligned16(I) && aligned16(dQ), B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: alignment");
@@ -303,28 +306,11 @@ static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, con
         return set_error(B2R_E_UNSUPPORTED, "b2r_bprmf_fused_fwd_bwd: no fused variant for d=%d C=%d", d, C);
     const int SPB = GPC / GPS;
     const int64_t need = ((int64_t)B + SPB - 1) / SPB;          // passes
-    const int64_t cap = (int64_t)sm_count() * 2;                // persistent: 2 resident CTAs per SM, each pipelined
-    const int grid = (int)(need < cap ? need : cap);
-    static int stop = -1;
-    if (stop < 0) {
-        const char* e = getenv("B2R_FUSED_STOP");
-        stop = e ? atoi(e) : 3;
-        if (stop < 1 || stop > 3) stop = 3;
-    }
-    static int grid_mul = -1;
-    if (grid_mul < 0) {
-        const char* e = getenv("B2R_FUSED_GRID");
-        grid_mul = e ? atoi(e) : 6;
-        if (grid_mul < 1 || grid_mul > 32) grid_mul = 6;
-    }
-    const int64_t cap2 = (int64_t)sm_count() * grid_mul;
+    const int64_t cap2 = (int64_t)sm_count() * 6;               // measured best: 6 CTAs per SM in the queue
     const int grid2 = (int)(need < cap2 ? need : cap2);
-#define B2R_FUSED(LPR, R)                                                                              \
-    do {                                                                                               \
-        if (stop == 1) k_bprmf_fused<LPR, R, 1><<<grid2, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, GPS, err_flag, loss_out, done_counter); \
-        else if (stop == 2) k_bprmf_fused<LPR, R, 2><<<grid2, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, GPS, err_flag, loss_out, done_counter); \
-        else k_bprmf_fused<LPR, R, 3><<<grid2, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, B, C, GPS, err_flag, loss_out, done_counter); \
-    } while (0)
+#define B2R_FUSED(LPR, R)                                                                                          \
+    k_bprmf_fused<LPR, R, 3><<<grid2, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, qout, B, \
+                                                   C, GPS, err_flag, loss_out, done_counter)
     if (d == 32) {
         if (RPG == 2) B2R_FUSED(8, 2); else if (RPG == 4) B2R_FUSED(8, 4); else B2R_FUSED(8, 8);
     } else if (d == 64) {

@@ -7,6 +7,8 @@
 // a library-owned non-blocking stream while the HBM-bound kernels of the current step run; joins are event
 // waits, never host synchronisations.  Plans (bucket partitions, bucket.cu) are double-buffered in the caller-provided
 // workspace.  d must be 32, 64 or 128 (the widths the bucket kernels are built for).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64_t n_users, const float* I,
@@ -15,8 +17,9 @@ extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64
                                        b2r_stream_t stream);
 
 int b2r_bprmf_fused_fwd_bwd_loss(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
-                                 int64_t n_items, float* grad_pred, float* row_loss, float* dQ, int B, int C, int d,
-                                 int32_t* err_flag, float* loss_out, unsigned int* done_counter, b2r_stream_t stream);
+                                 int64_t n_items, float* grad_pred, float* row_loss, float* dQ, float* qout, int B, int C,
+                                 int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter,
+                                 b2r_stream_t stream);
 
 namespace b2r {
 
@@ -60,7 +63,7 @@ struct StepCtx {
     int64_t n_users, n_items;
     StepLayout L;
     char* ws;
-    cudaStream_t side;
+    cudaStream_t side;                // builds the plan of the next batch
     cudaEvent_t fork, join[2];
     int slot;                         // plan buffer the NEXT step will read if it was prefetched
     const void* pre_uid;
@@ -193,17 +196,15 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
     }
     c->slot = cur ^ 1;
 
-    // main: forward + loss + query-side backward
+    // main: forward + loss + query-side backward; the gathered user rows are kept in q (the item gradient's source)
+    float* q = reinterpret_cast<float*>(base + c->L.q);
     profile_begin(B2R_PROF_SCORE_FWD, main_s);
-    rc = b2r_bprmf_fused_fwd_bwd_loss(t->U, uid, t->n_users, t->I, iid, t->n_items, g, rows, dQ, B, C, d, err_flag, loss_out,
-                                      reinterpret_cast<unsigned int*>(base + c->L.counter), main_s);
+    rc = b2r_bprmf_fused_fwd_bwd_loss(t->U, uid, t->n_users, t->I, iid, t->n_items, g, rows, dQ, q, B, C, d, err_flag,
+                                      loss_out, reinterpret_cast<unsigned int*>(base + c->L.counter), main_s);
     const bool fused = (rc == 0);
     if (rc != 0 && rc != B2R_E_UNSUPPORTED) return rc;
     if (fused) profile_end(B2R_PROF_SCORE_FWD, main_s);
-    const float* item_src = t->U;           // dI = g * U[uid[b]]  (U is updated only after the item table)
-    const int64_t* item_src_id = uid;
     if (!fused) {
-        float* q = reinterpret_cast<float*>(base + c->L.q);
         rc = b2r_gather_rows(t->U, uid, t->n_users, q, B, d, err_flag, main_s);
         if (rc != 0) return rc;
         rc = b2r_rowdot_fwd(q, nullptr, B, t->I, iid, t->n_items, pred, B, C, d, err_flag, main_s);
@@ -217,22 +218,19 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
         rc = b2r_rowdot_bwd_query(g, t->I, iid, t->n_items, dQ, B, C, d, main_s);
         if (rc != 0) return rc;
         profile_end(B2R_PROF_SCORE_BWDQ, main_s);
-        item_src = q;
-        item_src_id = nullptr;
     }
 
-    // join plan(t), then the fused backward+optimizer on each table (item table first: it reads U rows)
+    // join plan(t); then the fused backward+optimizer on both tables in one launch: dI = g * q reads the saved user
+    // rows, so the two updates are independent and the small user-table job runs underneath the item-table job
     B2R_CUDA_OK(cudaStreamWaitEvent(main_s, c->join[cur], 0));
     const PlanBuf& p = c->L.plan[cur];
-    b2r_grad_source si{item_src, g, item_src_id, n, C, 0};
+    const b2r_grad_source su{dQ, nullptr, nullptr, B, 1, 0};
+    const b2r_grad_source si{q, g, nullptr, n, C, 0};
+    const b2r_apply_job ji{base + p.iws, n, t->n_items, &si, nullptr, nullptr, t->I, t->Im, t->Iv};
+    const b2r_apply_job ju{base + p.uws, B, t->n_users, &su, nullptr, nullptr, t->U, t->Um, t->Uv};
     profile_begin(B2R_PROF_SEGMENT_I, main_s);
-    rc = b2r_bucket_apply(base + p.iws, n, t->n_items, d, &si, nullptr, 2, nullptr, t->I, t->Im, t->Iv, opt, main_s);
+    rc = b2r_bucket_apply_pair(&ji, &ju, d, 2, opt, main_s);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_SEGMENT_I, main_s);
-    b2r_grad_source su{dQ, nullptr, nullptr, B, 1, 0};
-    profile_begin(B2R_PROF_SEGMENT_U, main_s);
-    rc = b2r_bucket_apply(base + p.uws, B, t->n_users, d, &su, nullptr, 2, nullptr, t->U, t->Um, t->Uv, opt, main_s);
-    if (rc != 0) return rc;
-    profile_end(B2R_PROF_SEGMENT_U, main_s);
     return 0;
 }

@@ -306,28 +306,78 @@ k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const in
     }
 }
 
-// Rows with many contributions (listed by k_bucket_sort): the whole CTA reduces one row -- contribution t goes to
-// group t % GPC, partials are combined in group order -> deterministic.  Normally the list is empty.
+// One table's share of an apply launch: the sorted pairs and row heads of its plan, its contribution sources and
+// the arrays to update.  `grid` CTAs of the launch work on it.
+struct ApplyJob {
+    const uint64_t* pairs;
+    const uint4* heads;
+    const int* n_heads;
+    const int* n_long;
+    const uint2* longs;
+    int long_cap;
+    int grid;
+    BSrc s0, s1;
+    float* W;
+    float* M;
+    float* V;
+    float* dense;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// k_apply_sorted: one lane group per touched row (the head list written by k_bucket_sort): request the weight/state
+// rows, sum the row's contributions in ascending position -- the first one is named by the head entry itself, so a
+// row with a single contribution never reads the pair array -- and apply the update.  No barriers, no atomics.
+// Rows with >= kLong contributions (listed by the sort; normally none) are then reduced by whole CTAs: contribution
+// t goes to group t % GPC, partials are combined in group order -> deterministic.
+// A launch can carry two jobs (two tables of one step): CTAs [0, a.grid) work on job a, the rest on job b, so a small
+// table's update runs underneath a large one's instead of as a separate, latency-bound launch.
+// ---------------------------------------------------------------------------------------------------
 template <int LPR, int MODE>
-__device__ __forceinline__ void apply_long_rows(const uint64_t* __restrict__ pairs, const int* __restrict__ n_long_ptr,
-                                                const uint2* __restrict__ longs, int long_cap, const BSrc& s0,
-                                                const BSrc& s1, float* W, float* M, float* V, float* dense,
-                                                const OptK& opt, float4 (*part)[LPR]) {
+__device__ __forceinline__ void apply_job(const ApplyJob& J, const OptK& opt, int bid, float4 (*part)[LPR]) {
     constexpr int D = LPR * 4;
     constexpr int GPC = kBT / LPR;
     const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
-    const int n_long = min(*n_long_ptr, long_cap);
-    for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
-        const uint2 e = longs[q];
+    const int sld = opt.state_ld ? opt.state_ld : D;
+    const int n_heads = *J.n_heads;
+    for (int h = bid * GPC + grp; h < n_heads; h += J.grid * GPC) {
+        const uint4 e = __ldg(J.heads + h);
+        const int len = (int)e.w;
+        if (len == 0) continue;                // long row: handled below
+        const int64_t row = (int64_t)e.x;
+        float4 w, m, v;
+        if (MODE == 2) {
+            w = ld4(J.W + row * D + sub * 4);
+            if (opt.kind == 1) m = ld4(J.M + row * sld + sub * 4);
+            if (opt.kind != 0) v = ld4(J.V + row * sld + sub * 4);
+        } else {
+            w = ld4(J.dense + row * D + sub * 4);
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t pos = e.y;
+        for (int t = 0;;) {
+            const float* base;
+            int ld;
+            int64_t r;
+            float c;
+            b_contribution(J.s0, J.s1, pos, base, ld, r, c);
+            fma4(acc, c, ld4(base + r * ld + sub * 4));
+            if (++t >= len) break;
+            pos = (uint32_t)J.pairs[e.z + t];
+        }
+        RowIO<LPR>::template finish<MODE>(row, acc, sub, w, m, v, J.W, J.M, J.V, J.dense, opt);
+    }
+    const int n_long = min(*J.n_long, J.long_cap);
+    for (int q = bid; q < n_long; q += J.grid) {
+        const uint2 e = J.longs[q];
         const int j0 = (int)e.x, len = (int)e.y;
-        const int64_t row = (int64_t)(pairs[j0] >> 32);
+        const int64_t row = (int64_t)(J.pairs[j0] >> 32);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = grp; t < len; t += GPC) {
             const float* base;
             int ld;
             int64_t r;
             float c;
-            b_contribution(s0, s1, (uint32_t)pairs[j0 + t], base, ld, r, c);
+            b_contribution(J.s0, J.s1, (uint32_t)J.pairs[j0 + t], base, ld, r, c);
             fma4(acc, c, ld4(base + r * ld + sub * 4));
         }
         part[grp][sub] = acc;
@@ -340,62 +390,24 @@ __device__ __forceinline__ void apply_long_rows(const uint64_t* __restrict__ pai
             }
             float4 w, m, v;
             if (MODE == 2) {
-                w = ld4(W + row * D + sub * 4);
-                if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-                if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
+                w = ld4(J.W + row * D + sub * 4);
+                if (opt.kind == 1) m = ld4(J.M + row * sld + sub * 4);
+                if (opt.kind != 0) v = ld4(J.V + row * sld + sub * 4);
             } else {
-                w = ld4(dense + row * D + sub * 4);
+                w = ld4(J.dense + row * D + sub * 4);
             }
-            RowIO<LPR>::template finish<MODE>(row, tot, sub, w, m, v, W, M, V, dense, opt);
+            RowIO<LPR>::template finish<MODE>(row, tot, sub, w, m, v, J.W, J.M, J.V, J.dense, opt);
         }
         __syncthreads();
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// k_apply_sorted: one lane group per touched row (the head list written by k_bucket_sort): request the weight/state
-// rows, sum the row's contributions in ascending position -- the first one is named by the head entry itself, so a
-// row with a single contribution never reads the pair array -- and apply the update.  No shared memory, no
-// barriers, no atomics.  Rows with >= kLong contributions are reduced afterwards by whole CTAs.
-// ---------------------------------------------------------------------------------------------------
 template <int LPR, int MODE>
 __global__ void __launch_bounds__(kBT)
-k_apply_sorted(const uint64_t* __restrict__ pairs, const uint4* __restrict__ heads, const int* __restrict__ n_heads_ptr,
-               const int* __restrict__ n_long_ptr, const uint2* __restrict__ longs, int long_cap, BSrc s0, BSrc s1,
-               float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, float* __restrict__ dense, OptK opt) {
-    constexpr int D = LPR * 4;
-    constexpr int GPC = kBT / LPR;
-    __shared__ float4 part[GPC][LPR];          // only touched when the batch has rows with >= kLong contributions
-    const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
-    const int n_heads = *n_heads_ptr;
-    for (int h = blockIdx.x * GPC + grp; h < n_heads; h += gridDim.x * GPC) {
-        const uint4 e = __ldg(heads + h);
-        const int len = (int)e.w;
-        if (len == 0) continue;                // long row: handled below
-        const int64_t row = (int64_t)e.x;
-        float4 w, m, v;
-        if (MODE == 2) {
-            w = ld4(W + row * D + sub * 4);
-            if (opt.kind == 1) m = ld4(M + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-            if (opt.kind != 0) v = ld4(V + row * (opt.state_ld ? opt.state_ld : D) + sub * 4);
-        } else {
-            w = ld4(dense + row * D + sub * 4);
-        }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t pos = e.y;
-        for (int t = 0;;) {
-            const float* base;
-            int ld;
-            int64_t r;
-            float c;
-            b_contribution(s0, s1, pos, base, ld, r, c);
-            fma4(acc, c, ld4(base + r * ld + sub * 4));
-            if (++t >= len) break;
-            pos = (uint32_t)pairs[e.z + t];
-        }
-        RowIO<LPR>::template finish<MODE>(row, acc, sub, w, m, v, W, M, V, dense, opt);
-    }
-    apply_long_rows<LPR, MODE>(pairs, n_long_ptr, longs, long_cap, s0, s1, W, M, V, dense, opt, part);
+k_apply_sorted(const __grid_constant__ ApplyJob a, const __grid_constant__ ApplyJob b, const __grid_constant__ OptK opt) {
+    __shared__ float4 part[kBT / LPR][LPR];    // only touched when the batch has rows with >= kLong contributions
+    if ((int)blockIdx.x < a.grid) apply_job<LPR, MODE>(a, opt, (int)blockIdx.x, part);
+    else apply_job<LPR, MODE>(b, opt, (int)blockIdx.x - a.grid, part);
 }
 
 struct BucketGeom {
@@ -403,7 +415,7 @@ struct BucketGeom {
 };
 
 static BucketGeom bucket_geom(int64_t n, int64_t n_rows) {
-    int64_t target = n / 192;                      // ~192 pairs per bucket ...
+    int64_t target = n / 192;                      // ~192 pairs per bucket (measured: 128 equal, 96 and below slower) ...
     if (target < 256) target = n / 32;             // ... but at least a few hundred buckets for small batches
     if (target < 1) target = 1;
     if (target > 32768) target = 32768;
@@ -511,45 +523,68 @@ extern "C" int b2r_bucket_partition(const int64_t* ids, int64_t n, int64_t n_row
     return 0;
 }
 
-extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d, const b2r_grad_source* s0,
-                                const b2r_grad_source* s1, int mode, float* dense, float* W, float* m, float* v,
-                                const b2r_optim* opt, b2r_stream_t stream) {
-    B2R_REQUIRE(ws && s0 && s0->src, B2R_E_BADARG, "b2r_bucket_apply: null pointer");
-    B2R_REQUIRE(s0->n + (s1 ? s1->n : 0) == n, B2R_E_BADARG, "b2r_bucket_apply: sources cover %lld of %lld positions",
-                (long long)(s0->n + (s1 ? s1->n : 0)), (long long)n);
-    B2R_REQUIRE(d == 32 || d == 64 || d == 128, B2R_E_UNSUPPORTED, "b2r_bucket_apply: d=%d (have 32, 64, 128)", d);
-    b2r_optim o{};
+// fills one job from the C-ABI arguments (validated); grid = CTAs it gets
+static int make_job(const b2r_apply_job* j, int d, int mode, const b2r_optim& o, int grid_cap, ApplyJob* out) {
+    B2R_REQUIRE(j->ws && j->s0 && j->s0->src, B2R_E_BADARG, "b2r_bucket_apply: null pointer");
+    B2R_REQUIRE(j->s0->n + (j->s1 ? j->s1->n : 0) == j->n, B2R_E_BADARG,
+                "b2r_bucket_apply: sources cover %lld of %lld positions",
+                (long long)(j->s0->n + (j->s1 ? j->s1->n : 0)), (long long)j->n);
     if (mode == 1) {
-        B2R_REQUIRE(dense, B2R_E_BADARG, "b2r_bucket_apply: mode 1 needs dense");
-    } else if (mode == 2) {
-        B2R_REQUIRE(W && opt, B2R_E_BADARG, "b2r_bucket_apply: mode 2 needs W and opt");
+        B2R_REQUIRE(j->dense, B2R_E_BADARG, "b2r_bucket_apply: mode 1 needs dense");
+    } else {
+        B2R_REQUIRE(j->W, B2R_E_BADARG, "b2r_bucket_apply: mode 2 needs W");
+        B2R_REQUIRE(o.kind != 1 || (j->m && j->v), B2R_E_BADARG, "b2r_bucket_apply: Adam needs m and v");
+        B2R_REQUIRE(o.kind != 2 || j->v, B2R_E_BADARG, "b2r_bucket_apply: Adagrad needs v");
+    }
+    B2R_REQUIRE(b2r_bucket_workspace_bytes(j->n, j->n_rows) != 0, B2R_E_UNSUPPORTED,
+                "b2r_bucket_apply: n=%lld n_rows=%lld unsupported", (long long)j->n, (long long)j->n_rows);
+    const BucketGeom g = bucket_geom(j->n, j->n_rows);
+    const BucketLayout L = bucket_layout(j->n, j->n_rows);
+    const char* base = static_cast<const char*>(j->ws);
+    const int* off = reinterpret_cast<const int*>(base + L.off);
+    out->pairs = reinterpret_cast<const uint64_t*>(base + L.pairs);
+    out->heads = reinterpret_cast<const uint4*>(base + L.heads);
+    out->n_heads = off + g.nb + 3;                   // touched rows, listed by k_bucket_sort
+    out->n_long = off + g.nb + 2;
+    out->longs = reinterpret_cast<const uint2*>(base + L.longs);
+    out->long_cap = L.long_cap;
+    out->s0 = to_bsrc(j->s0, d);
+    out->s1 = to_bsrc(j->s1, d);
+    out->W = j->W; out->M = j->m; out->V = j->v; out->dense = j->dense;
+    const int gpc = kBT / (d / 4);
+    int64_t need = (j->n + gpc - 1) / gpc;
+    if (need > grid_cap) need = grid_cap;
+    out->grid = (int)(need < 1 ? 1 : need);
+    return 0;
+}
+
+extern "C" int b2r_bucket_apply_pair(const b2r_apply_job* ja, const b2r_apply_job* jb, int d, int mode,
+                                     const b2r_optim* opt, b2r_stream_t stream) {
+    B2R_REQUIRE(ja, B2R_E_BADARG, "b2r_bucket_apply: null job");
+    B2R_REQUIRE(d == 32 || d == 64 || d == 128, B2R_E_UNSUPPORTED, "b2r_bucket_apply: d=%d (have 32, 64, 128)", d);
+    B2R_REQUIRE(mode == 1 || mode == 2, B2R_E_BADARG, "b2r_bucket_apply: mode %d (1 = dense +=, 2 = optimizer)", mode);
+    b2r_optim o{};
+    if (mode == 2) {
+        B2R_REQUIRE(opt, B2R_E_BADARG, "b2r_bucket_apply: mode 2 needs opt");
         o = *opt;
         B2R_REQUIRE(o.kind >= 0 && o.kind <= 2, B2R_E_BADARG, "b2r_bucket_apply: optimizer kind %d", o.kind);
-        B2R_REQUIRE(o.kind != 1 || (m && v), B2R_E_BADARG, "b2r_bucket_apply: Adam needs m and v");
-        B2R_REQUIRE(o.kind != 2 || v, B2R_E_BADARG, "b2r_bucket_apply: Adagrad needs v");
-    } else {
-        return set_error(B2R_E_BADARG, "b2r_bucket_apply: mode %d (1 = dense +=, 2 = optimizer)", mode);
     }
-    cudaStream_t s = as_stream(stream);
-    const BucketGeom g = bucket_geom(n, n_rows);
-    const BucketLayout L = bucket_layout(n, n_rows);
-    const char* base = static_cast<const char*>(ws);
-    const int* off = reinterpret_cast<const int*>(base + L.off);
-    const uint64_t* pairs = reinterpret_cast<const uint64_t*>(base + L.pairs);
-    const BSrc a = to_bsrc(s0, d), b = to_bsrc(s1, d);
+    ApplyJob a{}, b{};
+    const int cap = sm_count() * 16;
+    int rc = make_job(ja, d, mode, o, cap, &a);
+    if (rc != 0) return rc;
+    if (jb != nullptr) {
+        // the second job is the small one by convention; its CTAs come first in the grid so that they are placed at once
+        rc = make_job(jb, d, mode, o, cap, &b);
+        if (rc != 0) return rc;
+    } else {
+        b = a;
+        b.grid = 0;
+    }
     const OptK ok = make_optk(o);
-    const uint2* longs = reinterpret_cast<const uint2*>(base + L.longs);
-    const int* n_heads = off + g.nb + 3;             // touched rows, listed by k_bucket_sort
-    const uint4* heads = reinterpret_cast<const uint4*>(base + L.heads);
-    const int* n_long = off + g.nb + 2;
-#define B2R_BK(LPR, MODE)                                                                              \
-    do {                                                                                               \
-        constexpr int GPC = kBT / LPR;                                                                 \
-        int64_t need = (n + GPC - 1) / GPC;                                                            \
-        const int64_t cap = (int64_t)sm_count() * 16;                                                  \
-        k_apply_sorted<LPR, MODE><<<(int)(need < cap ? need : cap), kBT, 0, s>>>(pairs, heads, n_heads, n_long, longs, L.long_cap, \
-                                                                                a, b, W, m, v, dense, ok);       \
-    } while (0)
+    cudaStream_t s = as_stream(stream);
+    const int grid = a.grid + b.grid;
+#define B2R_BK(LPR, MODE) k_apply_sorted<LPR, MODE><<<grid, kBT, 0, s>>>(b.grid ? b : a, b.grid ? a : b, ok)
     if (mode == 1) {
         if (d == 32) B2R_BK(8, 1); else if (d == 64) B2R_BK(16, 1); else B2R_BK(32, 1);
     } else {
@@ -558,4 +593,11 @@ extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d
 #undef B2R_BK
     B2R_LAUNCH_OK("k_apply_sorted");
     return 0;
+}
+
+extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d, const b2r_grad_source* s0,
+                                const b2r_grad_source* s1, int mode, float* dense, float* W, float* m, float* v,
+                                const b2r_optim* opt, b2r_stream_t stream) {
+    const b2r_apply_job j{ws, n, n_rows, s0, s1, dense, W, m, v};
+    return b2r_bucket_apply_pair(&j, nullptr, d, mode, opt, stream);
 }
