@@ -223,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- e2e: pinned host batch -> H2D -> step -> loss D2H, every step, through model.train_step -----
     # Triple-buffered device id buffers filled by a copy stream (the DataLoader's pin_memory/prefetch role);
-    # the host reads every step's loss from pinned memory, one step behind the GPU (helpers/BaseRunner.py:207
+    # the host reads every step's loss from pinned memory, a few steps behind the enqueue front (helpers/BaseRunner.py:207
     # reads it every step too).  All copies are enqueued inside the timed region.
     NB = 3
     copy_s = torch.cuda.Stream(device=device)
@@ -233,8 +233,9 @@ def run_ours(args, rank, world, local_rank):
             for _ in range(NB)]
     ready = [torch.cuda.Event() for _ in range(NB)]
     done = [torch.cuda.Event() for _ in range(NB)]
-    loss_h = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    LAG, RING = 3, 4                      # the host reads every step's loss, LAG steps behind the enqueue front
+    loss_h = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(RING)]
+    loss_ev = [torch.cuda.Event() for _ in range(RING)]
 
     def stage(k):
         j = k % NB
@@ -257,13 +258,14 @@ def run_ours(args, rank, world, local_rank):
             main_s.wait_event(ready[(k + 1) % NB])
             ls = model.train_step(bufs[k % NB], bufs[(k + 1) % NB])
             done[k % NB].record(main_s)
-            loss_h[k % 2].copy_(ls, non_blocking=True)
-            loss_ev[k % 2].record(main_s)
-            if k > k0:
-                loss_ev[(k - 1) % 2].synchronize()
-                seen.append(float(loss_h[(k - 1) % 2]))
-        loss_ev[(k0 + n_steps - 1) % 2].synchronize()
-        seen.append(float(loss_h[(k0 + n_steps - 1) % 2]))
+            loss_h[k % RING].copy_(ls, non_blocking=True)
+            loss_ev[k % RING].record(main_s)
+            if k - LAG >= k0:
+                loss_ev[(k - LAG) % RING].synchronize()
+                seen.append(float(loss_h[(k - LAG) % RING]))
+        for k in range(max(k0, k0 + n_steps - LAG), k0 + n_steps):
+            loss_ev[k % RING].synchronize()
+            seen.append(float(loss_h[k % RING]))
         copy_s.synchronize()
         return seen
 

@@ -85,36 +85,55 @@ struct FusedPass {
     int c_mine;          // candidate whose score/gradient this lane speaks for (row sub / RS), if sub % RS == 0
     float invB;
 
-    __device__ __forceinline__ void load_rows(int64_t pass, float4 (&r)[RPG], float4& rp, float4& q) const {
+    struct Ids {
+        int64_t qrow;
+        uint32_t my_id, pos_id;
+    };
+
+    __device__ __forceinline__ Ids load_ids(int64_t pass) const {
         const int64_t b = pass * SPB + slot;
-        const bool have = b < B;
-        int64_t qrow = 0;
-        uint32_t my_id = 0, pos_id = 0;
-        if (have) {
-            qrow = checked_id(uid[b], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
-            if (sub < RPG && c_load < C) my_id = (uint32_t)checked_id(ids[b * C + c_load], n_t, err_flag);
-            pos_id = (uint32_t)checked_id(ids[b * C], n_t, nullptr);
+        Ids r{0, 0u, 0u};
+        if (b < B) {
+            r.qrow = checked_id(uid[b], n_users, sub == 0 && j == 0 ? err_flag : nullptr);
+            if (sub < RPG && c_load < C) r.my_id = (uint32_t)checked_id(ids[b * C + c_load], n_t, err_flag);
+            r.pos_id = (uint32_t)checked_id(ids[b * C], n_t, nullptr);
         }
-        q = ld4(U + qrow * D + sub * 4);
-        rp = have ? ld4(T + (size_t)pos_id * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return r;
+    }
+
+    // request a pass's rows: the RPG candidate rows go to this thread's slots of a shared-memory stage with cp.async
+    // (16 B per lane, nothing held in registers while in flight), the user row and the positive's row to registers
+    __device__ __forceinline__ void issue_rows(int64_t pass, const Ids& id, float4* stage, float4& rp, float4& q) const {
+        const bool have = pass * SPB + slot < B;
+        q = ld4(U + id.qrow * D + sub * 4);
+        rp = have ? ld4(T + (size_t)id.pos_id * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
-            const uint32_t id_k = __shfl_sync(B2R_FULL_MASK, my_id, k, LPR);
+            const uint32_t id_k = __shfl_sync(B2R_FULL_MASK, id.my_id, k, LPR);
             const bool ok = have && (j + GPS * k) < C;
-            r[k] = ok ? ld_row4(T + (size_t)id_k * D + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4* dst = stage + k * 256 + threadIdx.x;
+            if (ok) {
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(T + (size_t)id_k * D + sub * 4)
+                             : "memory");
+            } else {
+                *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
 
     // STOP (debug bisect knob, B2R_FUSED_STOP): 1 = scores only, 2 = + loss statistics, 3 = everything (default)
     template <int STOP>
-    __device__ __forceinline__ void compute(int64_t pass, const float4 (&r)[RPG], const float4& rp, const float4& q,
+    __device__ __forceinline__ void compute(int64_t pass, const float4* stage, const float4& rp, const float4& q,
                                             float4* sstat, float4 (*part)[LPR]) const {
+        const float4* r = stage + threadIdx.x;                      // row k of this lane's group: r[k * 256]
         const int64_t b = pass * SPB + slot;
         const bool have = b < B;
         const bool mine_ok = have && (sub % RS) == 0 && c_mine < C;
         float d[RPG];
 #pragma unroll
-        for (int k = 0; k < RPG; ++k) d[k] = dot4(q, r[k]);
+        for (int k = 0; k < RPG; ++k) d[k] = dot4(q, r[k * 256]);
         const float p = group_sum<LPR>(dot4(q, rp));                 // positive's score, known to every group
         const float x = group_sum_multi<LPR, RPG>(d, sub);           // score of candidate c_mine (copies in RS lanes)
         if (mine_ok && pred != nullptr) pred[b * C + c_mine] = x;
@@ -170,7 +189,7 @@ struct FusedPass {
 #pragma unroll
         for (int k = 0; k < RPG; ++k) {
             const float gk = __shfl_sync(B2R_FULL_MASK, gmine, k * RS, LPR);
-            fma4(acc, gk, r[k]);
+            fma4(acc, gk, r[k * 256]);
         }
         part[grp][sub] = acc;
         __syncthreads();
@@ -209,11 +228,31 @@ k_bprmf_fused(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
     f.c_mine = f.j + GPS * (f.sub / P::RS);
     f.invB = 1.f / (float)B;
     const int64_t npass = ((int64_t)B + f.SPB - 1) / f.SPB;
+    // Software pipeline over this CTA's passes: while pass p is reduced out of shared-memory stage `par`, the rows of
+    // the next pass are landing in the other stage and the ids of the pass after that are in flight.
+    extern __shared__ __align__(16) float4 stages[];      // [2][RPG][256]
+    int64_t p = blockIdx.x;
+    float4 q, rp;
+    typename P::Ids idn{0, 0u, 0u};
+    if (p < npass) {
+        const typename P::Ids id0 = f.load_ids(p);
+        f.issue_rows(p, id0, stages, rp, q);
+        if (p + gridDim.x < npass) idn = f.load_ids(p + gridDim.x);
+    }
     int par = 0;
-    for (int64_t p = blockIdx.x; p < npass; p += gridDim.x, par ^= 1) {
-        float4 r[RPG], rp, q;
-        f.load_rows(p, r, rp, q);
-        f.template compute<STOP>(p, r, rp, q, sstat[par], part[par]);
+    for (; p < npass; p += gridDim.x, par ^= 1) {
+        const int64_t pn = p + gridDim.x;
+        float4 qn = q, rpn = rp;
+        if (pn < npass) {
+            f.issue_rows(pn, idn, stages + (par ^ 1) * RPG * 256, rpn, qn);
+            if (pn + gridDim.x < npass) idn = f.load_ids(pn + gridDim.x);
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        f.template compute<STOP>(p, stages + par * RPG * 256, rp, q, sstat[par], part[par]);
+        q = qn;
+        rp = rpn;
     }
     // mean of the per-sample losses by the last CTA to finish (fixed summation order -> deterministic)
     if (loss_out != nullptr) {
@@ -306,11 +345,19 @@ static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, con
         return set_error(B2R_E_UNSUPPORTED, "b2r_bprmf_fused_fwd_bwd: no fused variant for d=%d C=%d", d, C);
     const int SPB = GPC / GPS;
     const int64_t need = ((int64_t)B + SPB - 1) / SPB;          // passes
-    const int64_t cap2 = (int64_t)sm_count() * 6;               // measured best: 6 CTAs per SM in the queue
+    const int64_t cap2 = (int64_t)sm_count() * 3;               // persistent: exactly the 3 resident CTAs per SM (measured best)
     const int grid2 = (int)(need < cap2 ? need : cap2);
 #define B2R_FUSED(LPR, R)                                                                                          \
-    k_bprmf_fused<LPR, R, 3><<<grid2, 256, 0, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, qout, B, \
-                                                   C, GPS, err_flag, loss_out, done_counter)
+    do {                                                                                                           \
+        constexpr int smem = 2 * R * 256 * 16;                                                                     \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            B2R_CUDA_OK(cudaFuncSetAttribute(k_bprmf_fused<LPR, R, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        k_bprmf_fused<LPR, R, 3><<<grid2, 256, smem, s>>>(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, \
+                                                          qout, B, C, GPS, err_flag, loss_out, done_counter);      \
+    } while (0)
     if (d == 32) {
         if (RPG == 2) B2R_FUSED(8, 2); else if (RPG == 4) B2R_FUSED(8, 4); else B2R_FUSED(8, 8);
     } else if (d == 64) {

@@ -102,7 +102,12 @@ extern "C" int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t
     c->slot = 0;
     c->have_pre = false;
     c->pre_uid = c->pre_iid = nullptr;
-    cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    // The plan stream gets the highest priority: its kernels are small, and when the HBM-bound kernels of the main
+    // stream occupy every SM the plan's CTAs must be placed first whenever a slot frees up -- otherwise the plan of
+    // the next batch is starved and the next step's update waits for it (measured: 0.177 vs 0.199 ms per step).
+    int prio_lo = 0, prio_hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[1], cudaEventDisableTiming);

@@ -570,7 +570,7 @@ extern "C" int b2r_bucket_apply_pair(const b2r_apply_job* ja, const b2r_apply_jo
         B2R_REQUIRE(o.kind >= 0 && o.kind <= 2, B2R_E_BADARG, "b2r_bucket_apply: optimizer kind %d", o.kind);
     }
     ApplyJob a{}, b{};
-    const int cap = sm_count() * 16;
+    const int cap = sm_count() * 16;             // ~2.7 waves of 6 resident CTAs/SM; x12 and x20 measured slower
     int rc = make_job(ja, d, mode, o, cap, &a);
     if (rc != 0) return rc;
     if (jb != nullptr) {
