@@ -183,6 +183,13 @@ def run_ours(args, rank, world, local_rank):
             a.record(); b.record()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
+    # host cost of enqueuing one step with an empty launch queue (no back-pressure): 40 steps right after a sync
+    torch.cuda.synchronize()
+    h0 = time.perf_counter()
+    for k in range(40):
+        step_resident(k)
+    host_cost_ms = (time.perf_counter() - h0) * 1e3 / 40
+    torch.cuda.synchronize()
     sampler.start()
     time.sleep(0.3)                      # let nvidia-smi come up before the timed region
     launches0 = lib.b2r_launch_count()
@@ -236,6 +243,8 @@ def run_ours(args, rank, world, local_rank):
     LAG, RING = 3, 4                      # the host reads every step's loss, LAG steps behind the enqueue front
     loss_h = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(RING)]
     loss_ev = [torch.cuda.Event() for _ in range(RING)]
+    keep = [None] * RING                  # keeps each step's loss tensor alive until the host has read it
+    d2h_s = torch.cuda.Stream(device=device)
 
     def stage(k):
         j = k % NB
@@ -258,8 +267,13 @@ def run_ours(args, rank, world, local_rank):
             main_s.wait_event(ready[(k + 1) % NB])
             ls = model.train_step(bufs[k % NB], bufs[(k + 1) % NB])
             done[k % NB].record(main_s)
-            loss_h[k % RING].copy_(ls, non_blocking=True)
-            loss_ev[k % RING].record(main_s)
+            # the 4-byte loss read-back rides on its own stream: a D2H copy enqueued on the main stream would sit
+            # between this step's last kernel and the next step's first one
+            keep[k % RING] = ls
+            with torch.cuda.stream(d2h_s):
+                d2h_s.wait_event(done[k % NB])
+                loss_h[k % RING].copy_(ls, non_blocking=True)
+                loss_ev[k % RING].record(d2h_s)
             if k - LAG >= k0:
                 loss_ev[(k - LAG) % RING].synchronize()
                 seen.append(float(loss_h[(k - LAG) % RING]))
@@ -346,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2_policy": "inputs larger than L2: 512 MB tables + 1 GB Adam state, fresh ids every step"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": 8 * B + 8 * B * C,
                 "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / args.steps, 5)},
-        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms_step, 5), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms_step, 5), "host_cost_ms_per_step_empty_queue": round(host_cost_ms, 5), "clocks": clocks, "roofline": roofline, "kernels": kernels,
         "step_roofline": {"alg_bytes_per_step": int(step_alg), "achieved": round(step_alg / (ms_step * 1e-3) / 1e9, 1),
                           "frac": round(step_alg / (ms_step * 1e-3) / 1e9 / peak, 4),
                           "survey_8d_bytes_no_optimizer": int(survey_bytes)},
