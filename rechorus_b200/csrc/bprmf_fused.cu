@@ -1,14 +1,14 @@
 // bprmf_fused.cu -- K1+K2a in one pass: gather the user row and the (1+K) candidate rows, score them, evaluate
 // the BPR loss and its closed-form gradient, and reduce dQ = sum_c g_c * I[id_c] -- with every candidate row
-// read from HBM exactly once and kept in registers between the scoring and the gradient phase.
+// read from HBM exactly once: it is staged in shared memory by cp.async one pass ahead of its use and read from
+// there for the score and again for the gradient.
 //
 // Work decomposition: a sample is owned by GPS lane groups (GPS a power of two <= groups per CTA); group j takes
-// candidates c = j, j+GPS, j+2*GPS ... (at most RPG of them, all loaded before the first reduction -> RPG
-// independent 128-bit loads in flight per lane).  Scores meet in shared memory, every group then derives the
-// softmax/sigmoid statistics of its sample redundantly (C <= 256 values, cheaper than another barrier),
-// computes g for its own rows, accumulates g*row in registers, and the GPS partial dQ vectors are summed in
-// group order (deterministic).  replaces: BPRMF.py:39-42 forward, BaseModel.py:182-185 loss, and the
-// mul/sum + loss half of loss.backward() (BaseRunner.py:205).
+// candidates c = j, j+GPS, j+2*GPS ... (at most RPG of them).  Every group derives the positive's score itself, the
+// groups' softmax/sigmoid statistics meet in shared memory (online-softmax combine), each lane then has g for its own
+// candidate, the group accumulates g*row, and the GPS partial dQ vectors are summed in group order (deterministic).
+// replaces: BPRMF.py:39-42 forward, BaseModel.py:182-185 loss, and the mul/sum + loss half of loss.backward()
+// (BaseRunner.py:205).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -24,16 +24,6 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
-// A CTA walks passes p = blockIdx.x, += gridDim.x; a pass covers SPB = GPC/GPS samples.  Software pipeline, two
-// deep: while pass p is being reduced, the candidate rows of pass p+1 are in flight (second register set) and the
-// ids of pass p+2 are in flight (one register), so neither the id fetch nor the row fetch latency is exposed.
-// Phases of a pass (every thread works in every phase; each transcendental is evaluated once per candidate):
-//   dots: lane k of a group ends up holding the score of the group's k-th row
-//   A: per-sample max over the negatives          warp shuffle + shared memory, |barrier|
-//   B: e = exp(x-max), s = sigmoid(p-x) for the thread's own candidate; per-sample sums Z, A, D  |barrier|
-//   C: g for the own candidate (stored), broadcast inside the group, acc = sum g*row -> shared memory  |barrier|
-//   D: 4*LPR threads per sample add the GPS partials in group order -> dQ (deterministic)
-// Shared buffers alternate by pass parity, so no barrier is needed between passes.
 // sum each of the RPG per-lane values over the LPR lanes of a group with RPG + log2(LPR/RPG) shuffles instead of
 // RPG * log2(LPR): at every step the lanes split the live values in two halves and exchange the half they give up.
 // Afterwards lane `sub` holds the total of value sub / (LPR/RPG)  (lanes of one block of LPR/RPG hold copies).
@@ -123,7 +113,7 @@ struct FusedPass {
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
 
-    // STOP (debug bisect knob, B2R_FUSED_STOP): 1 = scores only, 2 = + loss statistics, 3 = everything (default)
+    // STOP (compile-time bisect knob): 1 = scores only, 2 = + loss statistics, 3 = everything (the product)
     template <int STOP>
     __device__ __forceinline__ void compute(int64_t pass, const float4* stage, const float4& rp, const float4& q,
                                             float4* sstat, float4 (*part)[LPR]) const {

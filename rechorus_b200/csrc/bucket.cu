@@ -8,11 +8,12 @@
 //         sorted exactly as a device-wide radix sort would leave it, at a fraction of the cost; rows with many
 //         contributions are listed for the cooperative kernel; buckets beyond the shared-memory capacity are
 //         chunk-sorted and merged.
+//         The sort also lists every touched row once: (row, first position, index of its first pair, run length).
 //   apply side (main stream):
-//     k_apply_sorted  one lane group per pair; the group holding the first pair of a row owns the row: requests
-//         w (m, v), walks the row's contributions in ascending position, applies SGD/Adam/Adagrad in place (mode 2)
-//         or adds into a dense gradient (mode 1).  No shared memory, no barriers, no atomics.
-//         Rows with >= kLong contributions (listed by the sort) are then reduced by whole CTAs in a fixed order.
+//     k_apply_sorted  one lane group per touched row (head list): requests w (m, v), sums the row's contributions in
+//         ascending position, applies SGD/Adam/Adagrad in place (mode 2) or adds into a dense gradient (mode 1).
+//         No barriers, no atomics.  Rows with >= kLong contributions (listed by the sort) are then reduced by whole
+//         CTAs in a fixed order.  A launch can carry two independent tables (jobs).
 // Every sum has a fixed order whatever order the partition's atomics produced -> same bits on every run.
 // Replaces ATen embedding_dense_backward + the dense grad zero-fill + the embedding part of optimizer.step()
 // (helpers/BaseRunner.py:193,205,206).

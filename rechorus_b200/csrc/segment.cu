@@ -348,12 +348,7 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
                                                                a, b, uniq_rows, grad_rows, dense, W, m, v, make_optk(o)); \
         }                                                                                              \
     } while (0)
-    static int rpi = -1;                 // tuning knob (B2R_SEG_RPI = 0 | 1 | 2 | 4), read once; 0 = one-row kernel
-    if (rpi < 0) {
-        const char* e = getenv("B2R_SEG_RPI");
-        rpi = e ? atoi(e) : 4;
-        if (rpi != 0 && rpi != 1 && rpi != 2 && rpi != 4) rpi = 4;
-    }
+    // rows per lane-group iteration of the optimizer kernel: 4 measured best at config 2 (1: +9 %, 2: +3 % step time)
 #define B2R_OPT(LPR, RPI)                                                                              \
     do {                                                                                               \
         constexpr int GPC = 256 / LPR;                                                                 \
@@ -363,17 +358,12 @@ extern "C" int b2r_segment_apply(const uint32_t* sorted_key, const uint32_t* sor
         k_segment_optim<LPR, RPI><<<grid, 256, 0, s>>>(sorted_key, sorted_pos, seg_start, n_uniq, nn, n_rows, a, b, \
                                                        W, m, v, make_optk(o));                         \
     } while (0)
-#define B2R_OPT_R(LPR)                                                                                 \
-    do {                                                                                               \
-        if (rpi == 1) B2R_OPT(LPR, 1); else if (rpi == 2) B2R_OPT(LPR, 2); else B2R_OPT(LPR, 4);       \
-    } while (0)
     if (mode == 0) B2R_SEG_D(0);
     else if (mode == 1) B2R_SEG_D(1);
-    else if (rpi != 0 && d == 32) B2R_OPT_R(8);
-    else if (rpi != 0 && d == 64) B2R_OPT_R(16);
-    else if (rpi != 0 && d == 128) B2R_OPT_R(32);
+    else if (d == 32) B2R_OPT(8, 4);
+    else if (d == 64) B2R_OPT(16, 4);
+    else if (d == 128) B2R_OPT(32, 4);
     else B2R_SEG_D(2);
-#undef B2R_OPT_R
 #undef B2R_OPT
 #undef B2R_SEG_D
 #undef B2R_SEG
