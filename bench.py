@@ -373,9 +373,18 @@ def run_ours(args, rank, world, local_rank):
 # CPU legs (the only place bench.py touches oracle/)
 # ------------------------------------------------------------------------------------------------------
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs are meant to use the box's cores (the physical
+    ones: half of os.cpu_count() on an SMT host, torch's own default), and only rank 0 runs them."""
+    want = max(1, (os.cpu_count() or 2) // 2)
+    if torch.get_num_threads() < want:
+        torch.set_num_threads(want)
+
+
 def run_cpu_reference(w, steps, warmup, batch_B=None, seed=1000):
     """The reference's own CPU step (oracle port of helpers/BaseRunner.py:184-207 incl. dense Adam)."""
     from oracle import rechorus_oracle as O
+    _use_all_host_threads()
     B = batch_B or w["B"]
     g = torch.Generator().manual_seed(0)
     params = O.bprmf_init(w["n_users"], w["n_items"], w["d"], g)
