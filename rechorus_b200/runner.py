@@ -58,6 +58,9 @@ class BaseRunner:
         parser.add_argument("--main_metric", type=str, default="", help="Metric that selects the best model.")
         parser.add_argument("--fused_optimizer", type=int, default=0,
                             help="1: row-sparse fused SGD/Adam/Adagrad (rechorus_b200.optim) instead of torch.optim")
+        parser.add_argument("--fused_step", type=int, default=0,
+                            help="1 (with --fused_optimizer 1): models that offer train_step run every training step "
+                                 "as one C call (forward, loss, backward, optimizer; next batch's plan prefetched)")
         parser.add_argument("--device_metrics", type=int, default=0,
                             help="1: rank the ground truth on the GPU (model.eval_ranks) instead of copying predictions "
                                  "to the host for evaluate_method")
@@ -96,6 +99,7 @@ class BaseRunner:
         self.pin_memory = args.pin_memory
         self.fused_optimizer = getattr(args, "fused_optimizer", 0)
         self.device_metrics = getattr(args, "device_metrics", 0)
+        self.fused_step = getattr(args, "fused_step", 0)
         self.topk = [int(x) for x in args.topk.split(",")]
         self.metrics = [m.strip().upper() for m in args.metric.split(",")]
         self.main_metric = args.main_metric or f"{self.metrics[0]}@{self.topk[0]}"
@@ -158,6 +162,30 @@ class BaseRunner:
             best + 1, format_metric(dev_results[best]), self.time[1] - self.time[0]))
         model.load_model()
 
+    def _fit_whole_steps(self, dataset, epoch=-1) -> float:
+        """The same epoch with the loop body of helpers/BaseRunner.py:185-207 replaced by the model's single-call
+        ``train_step`` (forward + loss + backward + row-sparse optimizer in one C call, the next batch's index plan
+        prefetched).  Batches and RNG consumption are those of ``fit``: the per-row candidate permutation is still
+        drawn (so the torch RNG stream stays in step with the reference loop) but not applied -- it is a no-op for a
+        model whose candidates are scored independently, and the whole-step kernel wants the positive in column 0.
+        Losses stay on the device until the epoch ends (the reference syncs on every step)."""
+        model = dataset.model
+        dl = DataLoader(dataset, batch_size=self.batch_size, shuffle=True, num_workers=self.num_workers,
+                        collate_fn=dataset.collate_batch, pin_memory=bool(self.pin_memory))
+        it = iter(dl)
+        cur = next(it, None)
+        cur = batch_to_device(cur, model.device) if cur is not None else None
+        losses = []
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                nxt = batch_to_device(nxt, model.device)
+            torch.rand(*cur["item_id"].shape)                     # BaseRunner.py:189's draw, see above
+            same_shape = nxt is not None and nxt["item_id"].shape == cur["item_id"].shape
+            losses.append(model.train_step(cur, nxt if same_shape else None))
+            cur = nxt
+        return float(np.mean(torch.stack(losses).cpu().numpy())) if losses else float("nan")
+
     def fit(self, dataset, epoch=-1) -> float:
         """helpers/BaseRunner.py:174-208, step for step."""
         model = dataset.model
@@ -165,6 +193,8 @@ class BaseRunner:
             model.optimizer = self._build_optimizer(model)
         dataset.actions_before_epoch()
         model.train()
+        if self.fused_step and hasattr(model, "train_step") and isinstance(model.optimizer, RowSparseOptimizer):
+            return self._fit_whole_steps(dataset, epoch)
         losses = []
         dl = DataLoader(dataset, batch_size=self.batch_size, shuffle=True, num_workers=self.num_workers,
                         collate_fn=dataset.collate_batch, pin_memory=bool(self.pin_memory))

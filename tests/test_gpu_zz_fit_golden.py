@@ -57,3 +57,35 @@ def test_deep_models_two_epochs_track_reference_runner(case):
     for k in gold.files:
         if k.startswith("m:"):
             assert 0.0 <= metrics[k[2:]] <= 1.0 and abs(metrics[k[2:]] - float(gold[k])) <= 0.15, k
+
+
+def test_whole_step_fit_equals_autograd_fit_under_sgd():
+    """--fused_step 1 (BaseRunner.fit's loop body as one C call per batch, next plan prefetched, ragged last batch)
+    against the autograd-node route of --fused_optimizer 1 on the same batches: same row-sparse SGD, so the final
+    weights agree to rounding."""
+    import argparse
+    from rechorus_b200 import plugin
+    from rechorus_b200.runner import BaseRunner
+    out = {}
+    for tag, extra in (("nodes", []), ("steps", ["--fused_step", "1"])):
+        p = argparse.ArgumentParser()
+        p = BaseRunner.parse_runner_args(p)
+        p = plugin.BPRMF.parse_model_args(p)
+        a = p.parse_args(["--emb_size", "64", "--num_neg", "7", "--batch_size", "96", "--num_workers", "0", "--lr", "0.05",
+                          "--l2", "0", "--optimizer", "SGD", "--table_mode", "fused", "--fused_optimizer", "1", *extra])
+        a.device, a.model_path, a.log_file = torch.device("cuda", 0), "/tmp/_b2r_ws.pt", ""
+        corpus = fit_corpus.build()
+        torch.manual_seed(9)
+        model = plugin.BPRMF(a, corpus).to(a.device)
+        with torch.no_grad():
+            for prm in model.parameters():
+                prm.mul_(30.0)                       # gradients well above rounding
+        train = plugin.BPRMF.Dataset(model, corpus, "train")
+        runner = BaseRunner(a)
+        np.random.seed(11)
+        torch.manual_seed(11)
+        losses = [runner.fit(train, epoch=e + 1) for e in range(2)]
+        out[tag] = (losses, {k: v.detach().cpu() for k, v in model.state_dict().items()})
+    assert np.allclose(out["nodes"][0], out["steps"][0], rtol=0, atol=1e-6), (out["nodes"][0], out["steps"][0])
+    for k, v in out["nodes"][1].items():
+        assert (v - out["steps"][1][k]).abs().max() <= 2e-6, k
