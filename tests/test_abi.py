@@ -54,3 +54,26 @@ def test_no_cpu_fallback():
     from rechorus_b200.lib import B200RecError
     with pytest.raises(B200RecError):
         ops.rowdot(torch.zeros(2, 8), None, torch.zeros(4, 8), torch.zeros(2, 3, dtype=torch.int64))
+
+
+def test_header_is_plain_c99(tmp_path):
+    """the boundary is a C ABI: the header must compile as C (no C++-isms, no torch/CUDA types)"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "b200rec.h"\nint main(void) { b2r_apply_job j; b2r_optim o; (void)j; (void)o; return 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_eval_and_pair_entry_points_reject_bad_arguments(built_lib):
+    from rechorus_b200 import lib as L
+    h = L.load()
+    assert h.b2r_gt_rank(None, 4, 4, 4, None, None) == -1 and b"null pointer" in h.b2r_last_error()
+    assert h.b2r_rank_histogram(None, 4, 10, None, None) == -1
+    assert h.b2r_rank_all_items(None, 64, None, None, 4, 100, 64, None, None, 0, None, None, None, None) == -1
+    assert h.b2r_bucket_apply_pair(None, None, 64, 2, None, None) == -1
+    assert h.b2r_bucket_workspace_bytes(0, 10) == 0 and h.b2r_bucket_workspace_bytes(100, 1000) > 100 * 24
