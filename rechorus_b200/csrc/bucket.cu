@@ -36,6 +36,9 @@ constexpr int kCap = 2048;        // pairs a CTA sorts in shared memory (16 KB)
 constexpr int kLong = 48;         // rows with at least this many contributions are reduced by the whole CTA
 constexpr int kBT = 256;
 constexpr int kPad = 32;          // ints per bucket counter: one 128-byte line each (L2 atomics serialise per line)
+constexpr int kCountShift = 12;   // counting-sort candidate: buckets of at most 4096 rows ...
+constexpr int kCountRows = 1 << kCountShift;
+constexpr int kRunMax = 32;       // ... whose longest row has at most this many contributions
 
 __device__ __forceinline__ void b_contribution(const BSrc& s0, const BSrc& s1, uint32_t p, const float*& base,
                                                int& ld, int64_t& row, float& c) {
@@ -241,18 +244,129 @@ __device__ __forceinline__ void emit_row_heads(const uint64_t* a, int cnt, int b
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CANDIDATE for the next round (selected with B2R_NEXT=1, never measured, off by default): counting sort of a bucket.
+// The bitonic network costs 36-45 barrier-separated stages per bucket; a bucket's keys span only R = 2^shift rows, so
+// one shared-memory histogram over the rows gives every pair its row's start, an arrival-order slot inside the row,
+// and -- for free -- the row heads.  Rows with several contributions (a minority) are put in ascending position by
+// one thread each (insertion sort, at most kRunMax elements).  Returns false, having written nothing, when a row has
+// more than kRunMax contributions: the caller then runs the bitonic path.  Output is identical to the bitonic path
+// (same sorted array; the head list is a permutation of the same entries).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bucket_sort_counting(uint64_t* __restrict__ g, int cnt, int beg, uint32_t row0, int R,
+                                                     uint64_t* s, int* hist, int* scratch, int* n_heads,
+                                                     uint4* heads) {
+    constexpr int PER = kCap / kBT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int r = tid; r <= R; r += kBT) hist[r] = 0;
+    if (tid == 0) {
+        scratch[32] = 0;     // largest row count
+        scratch[33] = 0;     // head counter
+    }
+    __syncthreads();
+    uint64_t v[PER];
+    int rk[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid + q * kBT;
+        v[q] = 0;
+        rk[q] = 0;
+        if (i < cnt) {
+            v[q] = g[i];
+            rk[q] = atomicAdd(&hist[(uint32_t)(v[q] >> 32) - row0], 1);
+        }
+    }
+    __syncthreads();
+    // thread t owns rows [t * RP, (t + 1) * RP): largest count, then an exclusive scan across the CTA
+    const int RP = (R + kBT - 1) / kBT;
+    int local = 0, mx = 0;
+    for (int x = 0; x < RP; ++x) {
+        const int r = tid * RP + x;
+        if (r < R) {
+            const int c = hist[r];
+            local += c;
+            mx = max(mx, c);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(B2R_FULL_MASK, mx, o));
+    if (lane == 0) atomicMax(&scratch[32], mx);
+    int inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(B2R_FULL_MASK, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (scratch[32] > kRunMax) return false;             // same value in every thread
+    int run = inc - local;
+    for (int w = 0; w < warp; ++w) run += scratch[w];
+    for (int x = 0; x < RP; ++x) {
+        const int r = tid * RP + x;
+        if (r < R) {
+            const int c = hist[r];
+            hist[r] = run;                               // start of row r in the sorted bucket
+            run += c;
+        }
+    }
+    if (tid == 0) hist[R] = cnt;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid + q * kBT;
+        if (i < cnt) s[hist[(uint32_t)(v[q] >> 32) - row0] + rk[q]] = v[q];
+    }
+    __syncthreads();
+    int mine = 0;
+    for (int r = tid; r < R; r += kBT) {
+        const int a = hist[r], b = hist[r + 1];
+        for (int x = a + 1; x < b; ++x) {                // insertion sort of the row's run by (row, position)
+            const uint64_t val = s[x];
+            int y = x - 1;
+            while (y >= a && s[y] > val) {
+                s[y + 1] = s[y];
+                --y;
+            }
+            s[y + 1] = val;
+        }
+        mine += (b > a) ? 1 : 0;
+    }
+    if (mine) atomicAdd(&scratch[33], mine);
+    __syncthreads();
+    if (tid == 0) {
+        scratch[34] = atomicAdd(n_heads, scratch[33]);
+        scratch[33] = 0;
+    }
+    __syncthreads();
+    const int base = scratch[34];
+    for (int r = tid; r < R; r += kBT) {
+        const int a = hist[r], b = hist[r + 1];
+        if (b > a) {
+            const int slot = base + atomicAdd(&scratch[33], 1);
+            heads[slot] = make_uint4(row0 + (uint32_t)r, (uint32_t)s[a], (uint32_t)(beg + a), (uint32_t)(b - a));
+        }
+    }
+    for (int i = tid; i < cnt; i += kBT) g[i] = s[i];
+    __syncthreads();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_bucket_sort: one CTA per bucket sorts its (row, position) pairs in place.  Buckets cover ascending, disjoint
 // row ranges, so afterwards the whole pairs array is sorted by (row, position) -- the same order a device-wide
 // radix sort would give, at a fraction of its cost.  Rows with >= kLong contributions are listed for the
 // cooperative kernel.  Buckets larger than the shared-memory capacity (hot rows, tiny tables) are sorted in
 // kCap-sized chunks and then merged pairwise through the `tmp` array.
 // ---------------------------------------------------------------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(kBT)
 k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const int* __restrict__ off, int nb,
               int* __restrict__ n_long, uint2* __restrict__ longs, int long_cap, int* __restrict__ n_heads,
-              uint4* __restrict__ heads) {
+              uint4* __restrict__ heads, int shift) {
     __shared__ uint64_t s[kCap];
     __shared__ int head_cnt, head_base;
+    __shared__ int hist[COUNT ? kCountRows + 1 : 1];
+    __shared__ int scratch[COUNT ? 40 : 1];
     const int tid = threadIdx.x;
     if (tid == 0) head_cnt = 0;
     __syncthreads();
@@ -261,6 +375,9 @@ k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const in
         const int cnt = off[b + 1] - beg;
         if (cnt == 0) continue;
         uint64_t* g = pairs + beg;
+        if (COUNT && cnt <= kCap && shift <= kCountShift &&
+            bucket_sort_counting(g, cnt, beg, (uint32_t)b << shift, 1 << shift, s, hist, scratch, n_heads, heads))
+            continue;
         if (cnt <= kCap) {
             int P = 32;
             while (P < cnt) P <<= 1;
@@ -515,11 +632,18 @@ extern "C" int b2r_bucket_partition(const int64_t* ids, int64_t n, int64_t n_row
     k_bucket_scatter<<<grid, kBT, 0, s>>>(ids, n, n_rows, g.shift, ignore_id, ignore_n, cursor, pairs);
     B2R_LAUNCH_OK("k_bucket_scatter");
     const int sort_cap = sm_count() * 8;
-    k_bucket_sort<<<g.nb < sort_cap ? g.nb : sort_cap, kBT, 0, s>>>(pairs, reinterpret_cast<uint64_t*>(base + L.tmp), off,
-                                                                   g.nb, off + g.nb + 2,
-                                                                   reinterpret_cast<uint2*>(base + L.longs), L.long_cap,
-                                                                   off + g.nb + 3,
-                                                                   reinterpret_cast<uint4*>(base + L.heads));
+    // B2R_NEXT bit 0: counting-sort candidate for the next round (unmeasured; the default is the bitonic path)
+    static const int next_bits = [] { const char* e = getenv("B2R_NEXT"); return e ? atoi(e) : 0; }();
+    const int sort_grid = g.nb < sort_cap ? g.nb : sort_cap;
+    uint64_t* tmp = reinterpret_cast<uint64_t*>(base + L.tmp);
+    uint2* longs = reinterpret_cast<uint2*>(base + L.longs);
+    uint4* heads = reinterpret_cast<uint4*>(base + L.heads);
+    if (next_bits & 1)
+        k_bucket_sort<true><<<sort_grid, kBT, 0, s>>>(pairs, tmp, off, g.nb, off + g.nb + 2, longs, L.long_cap,
+                                                      off + g.nb + 3, heads, g.shift);
+    else
+        k_bucket_sort<false><<<sort_grid, kBT, 0, s>>>(pairs, tmp, off, g.nb, off + g.nb + 2, longs, L.long_cap,
+                                                       off + g.nb + 3, heads, g.shift);
     B2R_LAUNCH_OK("k_bucket_sort");
     return 0;
 }
