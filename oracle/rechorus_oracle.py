@@ -320,3 +320,49 @@ class ReferenceStyleTrainer:
         loss.backward()
         self.opt.step()
         return float(loss.detach())
+
+
+class LazyExactAdam:
+    """Reference for the NEXT optimizer mode of the kernels: row-sparse bookkeeping with the RESULTS of
+    the reference's dense ``torch.optim.Adam`` (helpers/BaseRunner.py:110-114,206).  Dense Adam keeps moving a row it
+    has no gradient for (momentum, and g = wd * w under weight decay); the row-sparse kernels of this round skip such
+    rows (SparseAdam semantics).  Here every row remembers the step it was last brought up to date and is advanced
+    through the skipped steps right before it is read by a forward pass or updated -- after ``flush()`` the table
+    equals dense Adam's (tests/test_oracle_golden.py::test_lazy_exact_adam_equals_dense_adam).  Pure-Python loops:
+    small cases only."""
+
+    def __init__(self, W: Tensor, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0):
+        self.W = W
+        self.m, self.v = torch.zeros_like(W), torch.zeros_like(W)
+        self.last = torch.zeros(W.shape[0], dtype=torch.long)
+        self.lr, (self.b1, self.b2), self.eps, self.wd = lr, betas, eps, weight_decay
+        self.t = 0
+
+    def _one(self, r: int, g: Tensor, t: int) -> None:
+        self.m[r] = self.b1 * self.m[r] + (1 - self.b1) * g
+        self.v[r] = self.b2 * self.v[r] + (1 - self.b2) * g * g
+        m_hat, v_hat = self.m[r] / (1 - self.b1 ** t), self.v[r] / (1 - self.b2 ** t)
+        self.W[r] -= self.lr * m_hat / (v_hat.sqrt() + self.eps)
+
+    def _advance(self, rows: Tensor, upto: int) -> None:
+        for r in rows.tolist():
+            for t in range(int(self.last[r]) + 1, upto + 1):
+                self._one(r, self.wd * self.W[r], t)
+            self.last[r] = max(int(self.last[r]), upto)
+
+    def read(self, rows: Tensor) -> Tensor:
+        """rows as the forward of step t+1 must see them"""
+        self._advance(torch.unique(rows), self.t)
+        return self.W[rows]
+
+    def step(self, rows: Tensor, grads: Tensor) -> None:
+        """rows unique, grads [len(rows), d]: the data gradient (weight decay is added here, like torch.optim.Adam)"""
+        self.t += 1
+        self._advance(rows, self.t - 1)
+        for i, r in enumerate(rows.tolist()):
+            self._one(r, grads[i] + self.wd * self.W[r], self.t)
+            self.last[r] = self.t
+
+    def flush(self) -> None:
+        self._advance(torch.arange(self.W.shape[0]), self.t)

@@ -76,3 +76,27 @@ def test_negative_sampler_rejects_clicked_items():
     clicked = {u: set(range(1, 40)) for u in range(5)}
     neg = O.sample_negatives([0, 1, 2, 3, 4] * 20, clicked, 50, 3, rng)
     assert neg.min() >= 40 and neg.max() < 50
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_lazy_exact_adam_equals_dense_adam(wd):
+    """the bookkeeping planned for the kernels' exact-Adam mode (advance a row through its skipped steps before it
+    is read or updated) reproduces the reference's dense torch.optim.Adam, forward reads included"""
+    torch.manual_seed(0)
+    n, d = 12, 5
+    W0 = torch.randn(n, d, dtype=torch.float64)
+    dense = W0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([dense], lr=1e-2, weight_decay=wd)
+    lazy = O.LazyExactAdam(W0.clone(), lr=1e-2, weight_decay=wd)
+    for _ in range(40):
+        rows = torch.unique(torch.randint(0, n, (3,)))
+        seen = lazy.read(rows)
+        assert torch.allclose(seen, dense.detach()[rows], rtol=0, atol=1e-12)
+        g = torch.randn(len(rows), d, dtype=torch.float64) * seen          # a gradient that depends on what was read
+        opt.zero_grad()
+        dense.grad = torch.zeros_like(dense)
+        dense.grad[rows] = g
+        opt.step()
+        lazy.step(rows, g)
+    lazy.flush()
+    assert (lazy.W - dense.detach()).abs().max() <= 1e-12
