@@ -275,6 +275,19 @@ B2R_API int b2r_colscale(const float* a, const float* w, float* out, int64_t row
 B2R_API int b2r_colsum_prod(const float* a, const float* b, float* out, int64_t rows, int d, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Groundwork for the exact dense-Adam mode (not used by the default paths of this round): advance rows of a table whose
+ * Adam state is kept row-sparsely through the optimizer steps they skipped, exactly as torch.optim.Adam over the whole
+ * table (helpers/BaseRunner.py:110-114,206) would have moved them with a zero data gradient (g = weight_decay * w).
+ * last [n_rows] int32 holds the step each row is up to date with.  rows == NULL: all n_rows rows (flush); otherwise n
+ * unique row ids.  Every processed row is brought to step `upto` and stamped max(upto, stamp) -- pass stamp = upto + 1
+ * when the step-(upto+1) update with b2r_bucket_apply / b2r_segment_apply follows.  opt carries lr, betas, eps,
+ * weight_decay, state_ld (kind must be Adam; bc1/bc2 are not used: every skipped step has its own).
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API int b2r_adam_exact_advance(const int64_t* rows, int64_t n, int64_t n_rows, int d, float* W, float* m, float* v,
+                                   int32_t* last, int upto, int stamp, const b2r_optim* opt, int32_t* err_flag,
+                                   b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Evaluation (row f2): integer ranks of the ground-truth item on the device.
  *
  * b2r_gt_rank:        rank[r] = #{c : pred[r*ld + c] >= pred[r*ld]}  -- helpers/BaseRunner.py:63 (column 0 is the

@@ -217,6 +217,24 @@ def rank_all_items(q: torch.Tensor, table: torch.Tensor, target: torch.Tensor,
     return rank
 
 
+def adam_exact_advance(W: torch.Tensor, m: torch.Tensor, v: torch.Tensor, last: torch.Tensor, upto: int, opt,
+                       rows: Optional[torch.Tensor] = None, stamp: int = 0, state_ld: int = 0) -> None:
+    """Groundwork for the exact dense-Adam mode (b2r_adam_exact_advance): bring the listed unique rows (all rows when
+    ``rows`` is None) of a row-sparsely updated table to optimizer step ``upto``, as torch.optim.Adam over the whole
+    table would have moved them on zero data gradients.  ``last`` int32 [n_rows] is read and re-stamped."""
+    _need_cuda(W, m, v, last, rows)
+    if last.dtype != torch.int32 or not last.is_contiguous():
+        raise TypeError("last must be a contiguous int32 tensor")
+    n = 0
+    if rows is not None:
+        rows = _i64c(rows.reshape(-1), "rows")
+        n = rows.numel()
+    o = _lib.Optim(1, opt.lr, opt.betas[0], opt.betas[1], opt.eps, opt.weight_decay, 1.0, 1.0, state_ld)
+    _lib.check(_lib.load().b2r_adam_exact_advance(_p(rows), n, W.shape[0], W.shape[1], _p(W), _p(m), _p(v), _p(last),
+                                                  int(upto), int(stamp), C.byref(o), _p(err_flag(W.device)), _stream()),
+               "b2r_adam_exact_advance")
+
+
 def bpr_loss_and_grad(pred: torch.Tensor, want_grad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """BaseModel.py:175-189 value and closed-form d loss / d pred in one pass."""
     _need_cuda(pred)

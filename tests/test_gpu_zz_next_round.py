@@ -1,0 +1,52 @@
+"""GPU tests of code that was written WITHOUT a GPU for the next round and is not part of any default
+path.  They are skipped unless B2R_NEXT is set (tools/gpu_next_round.sh sets it), so they cannot colour this round's
+results; the kernels selected by B2R_NEXT=1/2 themselves are exercised by the regular parity tests under that
+setting."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B2R_NEXT") is None, reason="next-round candidates: set B2R_NEXT to run")]
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_adam_exact_advance_equals_dense_adam_on_zero_gradients(d, wd):
+    """rows updated once, then left alone for k steps: b2r_adam_exact_advance must move them like torch.optim.Adam
+    over the whole table does (momentum, weight decay), listed rows only, then the flush form"""
+    from rechorus_b200 import ops
+    torch.manual_seed(d)
+    n = 200
+    W0 = torch.randn(n, d) * 0.1
+    dense = W0.clone().cuda().requires_grad_(True)
+    opt = torch.optim.Adam([dense], lr=1e-2, weight_decay=wd)
+    g0 = torch.zeros(n, d)
+    touched = torch.arange(0, n, 3)
+    g0[touched] = torch.randn(len(touched), d)
+    dense.grad = g0.cuda()
+    opt.step()                                              # step 1: the only data gradient
+    st = opt.state[dense]
+    W, m, v = dense.detach().clone(), st["exp_avg"].clone(), st["exp_avg_sq"].clone()
+    if wd == 0.0:                                           # a row-sparse table would not have touched the others
+        mask = torch.ones(n, dtype=torch.bool)
+        mask[touched] = False
+        assert float(m[mask.cuda()].abs().max()) == 0.0
+    last = torch.ones(n, dtype=torch.int32, device="cuda")
+    K = 37
+    for _ in range(K):                                      # steps 2 .. K+1 with zero data gradient everywhere
+        dense.grad = torch.zeros_like(dense)
+        opt.step()
+    cfg = types.SimpleNamespace(lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    some = touched[: len(touched) // 2].cuda()
+    ops.adam_exact_advance(W, m, v, last, K + 1, cfg, rows=some)
+    assert (W[some] - dense.detach()[some]).abs().max() <= 2e-6
+    assert int(last[some].min()) == K + 1 and int(last.max()) == K + 1
+    ops.adam_exact_advance(W, m, v, last, K + 1, cfg)       # flush: everything else
+    assert (W - dense.detach()).abs().max() <= 2e-6
+    assert (m - st["exp_avg"]).abs().max() <= 1e-6 and (v - st["exp_avg_sq"]).abs().max() <= 1e-6
+    assert int(last.min()) == K + 1
+    ops.check_ids()
