@@ -28,9 +28,16 @@ _DEFAULT_EPS = {"SGD": 0.0, "Adam": 1e-8, "Adagrad": 1e-10}
 
 class RowSparseOptimizer:
     def __init__(self, model: torch.nn.Module, name: str = "Adam", lr: float = 1e-3, l2: float = 0.0,
-                 betas=(0.9, 0.999), eps: float | None = None):
+                 betas=(0.9, 0.999), eps: float | None = None, exact_dense: bool = False):
+        """exact_dense (Adam only; next-round groundwork, not yet run on a GPU): keep the row-sparse cost but
+        reproduce the reference's dense torch.optim.Adam -- every fused table gets a per-row "up to date as of step"
+        stamp, rows are advanced through the steps they skipped before a forward reads them (``before_forward``)
+        and before they are updated, and ``flush()`` brings the whole table up to date (oracle.LazyExactAdam)."""
         if name not in _KIND:
             raise ValueError(f"optimizer {name!r} not supported by the fused path (have {sorted(_KIND)})")
+        if exact_dense and name != "Adam":
+            raise ValueError("exact_dense applies to Adam only (row-sparse SGD without weight decay already is exact)")
+        self.exact_dense = bool(exact_dense)
         self.name, self.kind = name, _KIND[name]
         self.lr, self.l2, self.betas = float(lr), float(l2), (float(betas[0]), float(betas[1]))
         self.eps = _DEFAULT_EPS[name] if eps is None else float(eps)
@@ -47,12 +54,37 @@ class RowSparseOptimizer:
                 # ([n_rows][2][d]) so each row's state is one contiguous 2*4d-byte burst in HBM
                 mv = torch.zeros((p.shape[0], 2, p.shape[1]), dtype=p.dtype, device=p.device)
                 e["mv"], e["m"], e["v"], e["state_ld"] = mv, mv[:, 0, :], mv[:, 1, :], 2 * p.shape[1]
+                if self.exact_dense:
+                    e["last"] = torch.zeros(p.shape[0], dtype=torch.int32, device=p.device)
             else:
                 if self.kind == _lib.OPT_ADAM:
                     e["m"] = torch.zeros_like(p.data)
                 if self.kind != _lib.OPT_SGD:
                     e["v"] = torch.zeros_like(p.data)
             self._entries.append(e)
+
+    # -- exact dense-Adam bookkeeping (exact_dense=True) ----------------------------------------------------
+    def _advance(self, e: dict, rows, upto: int, stamp: int = 0) -> None:
+        import types
+        cfg = types.SimpleNamespace(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=e["wd"])
+        ops.adam_exact_advance(e["p"].data, e["m"], e["v"], e["last"], upto, cfg, rows=rows, stamp=stamp,
+                               state_ld=e["state_ld"])
+
+    def before_forward(self, param: torch.Tensor, ids: torch.Tensor) -> None:
+        """bring the rows a forward pass is about to read up to the current step (no-op unless exact_dense)"""
+        if not self.exact_dense:
+            return
+        e = self.entry(param)
+        if "last" in e and self.t > 0:
+            self._advance(e, torch.unique(ids), self.t)
+
+    def flush(self) -> None:
+        """bring every row of every exact table up to the current step (before evaluation, saving, reading weights)"""
+        if not self.exact_dense:
+            return
+        for e in self._entries:
+            if "last" in e and self.t > 0:
+                self._advance(e, None, self.t)
 
     # -- torch.optim-like surface used by BaseRunner.fit ------------------------------------------------
     def zero_grad(self, set_to_none: bool = True) -> None:
@@ -84,6 +116,10 @@ class RowSparseOptimizer:
                     raise _lib.B200RecError(f"{e['name']}: two padded gradient streams into one table")
                 ids = pend[0][0] if len(pend) == 1 else torch.cat([pend[0][0], pend[1][0]])
                 ign = pend[0][2]
+                if "last" in e:
+                    # exact dense-Adam mode: the rows about to be updated must stand at step t-1 (they do already if
+                    # before_forward ran) and are stamped t, the step the update below applies
+                    self._advance(e, torch.unique(ids), self.t - 1, stamp=self.t)
                 plan = ops.make_plan(ids, p.shape[0], p.shape[1], ign, pend[0][0].numel() if ign >= 0 else 0)
                 plan.apply_optimizer(p.data, e["m"], e["v"], self._opt(e["wd"], e["state_ld"]), [x[1] for x in pend])
                 pend.clear()

@@ -131,6 +131,13 @@ class BPRMFKernels(_KernelModelMixin):
         self.check_list = []
         u_ids = feed_dict["user_id"]        # [B]
         i_ids = feed_dict["item_id"]        # [B, C]
+        opt = self.__dict__.get("_b2r_optimizer")
+        if getattr(opt, "exact_dense", False):                        # exact dense-Adam mode (next-round groundwork)
+            if self.training:
+                opt.before_forward(self.u_embeddings.weight, u_ids)
+                opt.before_forward(self.i_embeddings.weight, i_ids)
+            else:
+                opt.flush()
         u = ops.embedding(self.u_embeddings.weight, u_ids)            # [B, d]   (gather kernel)
         pred = ops.score(u, self.i_embeddings.weight, i_ids)          # [B, C]   (gather + dot kernel)
         return {"prediction": pred.view(feed_dict["batch_size"], -1)}
@@ -145,8 +152,9 @@ class BPRMFKernels(_KernelModelMixin):
         Needs ``self.optimizer`` to be a ``RowSparseOptimizer``.  ``next_feed_dict`` (optional) is the next
         batch, already on the device: its index plan is prefetched while this step runs.  Returns the loss as a
         device scalar."""
-        if self.emb_size not in (32, 64, 128):
-            # no bucket/fused kernel variant for this width: same step through the autograd nodes
+        if self.emb_size not in (32, 64, 128) or getattr(self.optimizer, "exact_dense", False):
+            # no bucket/fused kernel variant for this width (or the exact dense-Adam mode, which the single-call step
+            # does not implement yet): same step through the autograd nodes
             self.optimizer.zero_grad()
             loss = self.loss(self.forward(feed_dict))
             loss.backward()

@@ -61,6 +61,9 @@ class BaseRunner:
         parser.add_argument("--fused_step", type=int, default=0,
                             help="1 (with --fused_optimizer 1): models that offer train_step run every training step "
                                  "as one C call (forward, loss, backward, optimizer; next batch's plan prefetched)")
+        parser.add_argument("--exact_adam", type=int, default=0,
+                            help="1 (with --fused_optimizer 1, Adam): row-sparse cost, dense torch.optim.Adam results "
+                                 "(rows are advanced through their skipped steps; next-round groundwork)")
         parser.add_argument("--device_metrics", type=int, default=0,
                             help="1: rank the ground truth on the GPU (model.eval_ranks) instead of copying predictions "
                                  "to the host for evaluate_method")
@@ -100,6 +103,7 @@ class BaseRunner:
         self.fused_optimizer = getattr(args, "fused_optimizer", 0)
         self.device_metrics = getattr(args, "device_metrics", 0)
         self.fused_step = getattr(args, "fused_step", 0)
+        self.exact_adam = getattr(args, "exact_adam", 0)
         self.topk = [int(x) for x in args.topk.split(",")]
         self.metrics = [m.strip().upper() for m in args.metric.split(",")]
         self.main_metric = args.main_metric or f"{self.metrics[0]}@{self.topk[0]}"
@@ -121,7 +125,8 @@ class BaseRunner:
         logging.info("Optimizer: " + self.optimizer_name)
         if self.fused_optimizer:
             model.set_table_mode("fused")
-            return RowSparseOptimizer(model, self.optimizer_name, lr=self.learning_rate, l2=self.l2)
+            return RowSparseOptimizer(model, self.optimizer_name, lr=self.learning_rate, l2=self.l2,
+                                      exact_dense=bool(self.exact_adam))
         cls = getattr(torch.optim, self.optimizer_name)       # helpers/BaseRunner.py:112
         return cls(model.customize_parameters(), lr=self.learning_rate, weight_decay=self.l2)
 

@@ -50,3 +50,41 @@ def test_adam_exact_advance_equals_dense_adam_on_zero_gradients(d, wd):
     assert (m - st["exp_avg"]).abs().max() <= 1e-6 and (v - st["exp_avg_sq"]).abs().max() <= 1e-6
     assert int(last.min()) == K + 1
     ops.check_ids()
+
+
+@pytest.mark.parametrize("l2", [0.0, 1e-3])
+def test_exact_adam_mode_reproduces_dense_adam_training(l2):
+    """BPRMF trained for a number of steps through the plugin surface with RowSparseOptimizer(exact_dense=True): after
+    the flush the tables equal the reference-style training with dense torch.optim.Adam on the same batches (most
+    rows are skipped by most batches, so momentum / weight-decay catch-up is what is being tested)."""
+    import argparse
+    from oracle import rechorus_oracle as O
+    from rechorus_b200 import plugin
+    from rechorus_b200.optim import RowSparseOptimizer
+    p = plugin.BPRMF.parse_model_args(argparse.ArgumentParser())
+    a = p.parse_args(["--emb_size", "64", "--num_neg", "4", "--table_mode", "fused"])
+    a.device, a.model_path = torch.device("cuda", 0), "/tmp/_b2r_exact.pt"
+    corpus = types.SimpleNamespace(n_users=60, n_items=90)
+    torch.manual_seed(21)
+    model = plugin.BPRMF(a, corpus).to(a.device)
+    with torch.no_grad():
+        for prm in model.parameters():
+            prm.mul_(30.0)                                  # gradients well above rounding (Adam divides by |g|)
+    w0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    model.optimizer = RowSparseOptimizer(model, "Adam", lr=1e-2, l2=l2, exact_dense=True)
+    ref = O.ReferenceStyleTrainer("BPRMF", w0, lr=1e-2, l2=l2, optimizer="Adam")
+    g = torch.Generator().manual_seed(22)
+    model.train()
+    for step in range(25):
+        uid = torch.randint(1, 60, (8,), generator=g)
+        iid = torch.randint(1, 90, (8, 5), generator=g)
+        model.optimizer.zero_grad()
+        out = model({"user_id": uid.cuda(), "item_id": iid.cuda(), "batch_size": 8, "phase": "train"})
+        loss = model.loss(out)
+        loss.backward()
+        model.optimizer.step()
+        ref_loss = ref.step({"user_id": uid, "item_id": iid}, shuffle=False)
+        assert abs(float(loss) - ref_loss) <= 2e-5, (step, float(loss), ref_loss)
+    model.optimizer.flush()
+    for k, v in model.state_dict().items():
+        assert (v.cpu() - ref.p[k].detach()).abs().max() <= 2e-5, k
