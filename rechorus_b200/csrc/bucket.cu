@@ -622,7 +622,11 @@ extern "C" int b2r_bucket_partition(const int64_t* ids, int64_t n, int64_t n_row
     int* off = reinterpret_cast<int*>(base + L.off);
     uint64_t* pairs = reinterpret_cast<uint64_t*>(base + L.pairs);
     int grid = (int)((n + kBT * 4 - 1) / (kBT * 4));
-    const int cap = sm_count() * 8;
+    // next-round sweep knobs (unset = the measured configuration: 8 CTAs per SM for both): how much of each SM the
+    // side-stream plan kernels may occupy next to the HBM-bound kernels of the main stream
+    static const int part_mul = [] { const char* e = getenv("B2R_PART_CAP"); return e && atoi(e) > 0 ? atoi(e) : 8; }();
+    static const int sort_mul = [] { const char* e = getenv("B2R_SORT_CAP"); return e && atoi(e) > 0 ? atoi(e) : 8; }();
+    const int cap = sm_count() * part_mul;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     k_bucket_count<<<grid, kBT, 0, s>>>(ids, n, n_rows, g.shift, ignore_id, ignore_n, count, err_flag);
@@ -631,7 +635,7 @@ extern "C" int b2r_bucket_partition(const int64_t* ids, int64_t n, int64_t n_row
     B2R_LAUNCH_OK("k_bucket_scan");
     k_bucket_scatter<<<grid, kBT, 0, s>>>(ids, n, n_rows, g.shift, ignore_id, ignore_n, cursor, pairs);
     B2R_LAUNCH_OK("k_bucket_scatter");
-    const int sort_cap = sm_count() * 8;
+    const int sort_cap = sm_count() * sort_mul;
     // B2R_NEXT bit 0: counting-sort candidate for the next round (unmeasured; the default is the bitonic path)
     static const int next_bits = [] { const char* e = getenv("B2R_NEXT"); return e ? atoi(e) : 0; }();
     const int sort_grid = g.nb < sort_cap ? g.nb : sort_cap;

@@ -24,3 +24,8 @@ for r in rows[1:]:
     except: pass
 for k,v in agg.items(): print(f"  n={len(v):3d} avg={sum(v)/len(v)/1000:8.2f} us  {k}")
 PY
+# how much of each SM the plan kernels may take (default 8 CTAs/SM each): sweep with the best B2R_NEXT setting
+for SC in 2 4 8; do for PC in 4 8; do
+  B2R_SORT_CAP=$SC B2R_PART_CAP=$PC timeout 300 python bench.py --steps 600 --warmup 20 --no_cpu_baseline 2>/dev/null | tail -1 | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('sort_cap $SC part_cap $PC: ms %.4f apply %.4f plan %.4f fused %.4f'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['kernels']['plan_items']['ms'], d['kernels']['fused_score_loss_bwd']['ms']))"
+done; done
