@@ -275,6 +275,19 @@ B2R_API int b2r_colscale(const float* a, const float* w, float* out, int64_t row
 B2R_API int b2r_colsum_prod(const float* a, const float* b, float* out, int64_t rows, int d, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Groundwork for row f3 (not used by the default paths of this round): the per-epoch negative sampling of
+ * models/BaseModel.py:206-214 on the device.  out[i*K + j] is uniform over the items of [1, n_items) that are not in
+ * the training clicks of user_ids[i] (CSR: clicked_ptr [n_users+1], clicked_items sorted ascending and unique per user,
+ * all within [1, n_items)).  No rejection loop: with m clicks the user has A = n_items-1-m allowed items; r =
+ * floor(x * A / 2^32), x = word 0 of Philox4x32-10(counter = (lo32(i*K+j), hi32(i*K+j), 0, epoch), key = seed), and
+ * the (r+1)-th allowed item is found by one binary search over the click row.  Same distribution as the reference,
+ * NOT the same stream (NumPy's global Mersenne Twister consumed by a data-dependent Python loop).
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API int b2r_sample_negatives(const int64_t* user_ids, int64_t N, int K, const int64_t* clicked_ptr,
+                                 const int64_t* clicked_items, int64_t n_users, int64_t n_items, uint64_t seed,
+                                 uint32_t epoch, int64_t* out, int32_t* err_flag, b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Groundwork for the exact dense-Adam mode (not used by the default paths of this round): advance rows of a table whose
  * Adam state is kept row-sparsely through the optimizer steps they skipped, exactly as torch.optim.Adam over the whole
  * table (helpers/BaseRunner.py:110-114,206) would have moved them with a zero data gradient (g = weight_decay * w).

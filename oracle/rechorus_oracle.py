@@ -366,3 +366,42 @@ class LazyExactAdam:
 
     def flush(self) -> None:
         self._advance(torch.arange(self.W.shape[0]), self.t)
+
+
+# ------------------------------------------------------------------------------------------------------
+# device negative sampler (row f3 groundwork): the definition csrc/sampler.cu implements, restated
+# ------------------------------------------------------------------------------------------------------
+
+def philox4x32_10(ctr: Sequence[int], key: Sequence[int]) -> List[int]:
+    """Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123 reference
+    constants).  Pinned by the Random123 known-answer vectors in tests/test_oracle_golden.py."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c, k = list(ctr), list(key)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) & MASK) ^ c[1] ^ k[0], p1 & MASK, ((p0 >> 32) & MASK) ^ c[3] ^ k[1], p0 & MASK]
+        k = [(k[0] + W0) & MASK, (k[1] + W1) & MASK]
+    return c
+
+
+def device_sampler_reference(user_ids: Sequence[int], clicked: Dict[int, set], n_items: int, num_neg: int, seed: int,
+                             epoch: int) -> np.ndarray:
+    """What b2r_sample_negatives must return, bit for bit: uniform over the non-clicked items of [1, n_items)
+    (the distribution of models/BaseModel.py:206-214), drawn from the counter-based stream described in
+    include/b200rec.h instead of NumPy's global generator: one uniform r over the user's allowed items, mapped to
+    the (r+1)-th item of [1, n_items) that is not clicked."""
+    out = np.zeros((len(user_ids), num_neg), dtype=np.int64)
+    key = [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]
+    allowed_of: Dict[int, List[int]] = {}
+    for i, u in enumerate(user_ids):
+        u = int(u)
+        if u not in allowed_of:
+            seen = clicked.get(u, set())
+            assert all(1 <= c < n_items for c in seen)
+            allowed_of[u] = [c for c in range(1, n_items) if c not in seen]
+        allowed = allowed_of[u]
+        for j in range(num_neg):
+            idx = i * num_neg + j
+            x = philox4x32_10([idx & 0xFFFFFFFF, (idx >> 32) & 0xFFFFFFFF, 0, epoch], key)[0]
+            out[i, j] = allowed[(x * len(allowed)) >> 32]
+    return out

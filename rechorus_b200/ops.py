@@ -217,6 +217,37 @@ def rank_all_items(q: torch.Tensor, table: torch.Tensor, target: torch.Tensor,
     return rank
 
 
+class DeviceNegativeSampler:
+    """Groundwork for SURVEY.md §8 f3: models/BaseModel.py:206-214 on the device.  Holds the training clicks as a CSR
+    on the GPU and draws ``num_neg`` non-clicked items per training row with b2r_sample_negatives.  Same distribution
+    as the reference's NumPy loop, a different (counter-based, reproducible from (seed, epoch)) random stream."""
+
+    def __init__(self, train_clicked_set: dict, n_users: int, n_items: int, device, seed: int = 0):
+        import numpy as np
+        ptr = np.zeros(n_users + 1, dtype=np.int64)
+        for u, items in train_clicked_set.items():
+            if 0 <= int(u) < n_users:
+                ptr[int(u) + 1] = len(items)
+        ptr = np.cumsum(ptr)
+        flat = np.zeros(max(int(ptr[-1]), 1), dtype=np.int64)
+        for u, items in train_clicked_set.items():
+            if 0 <= int(u) < n_users and len(items):
+                flat[ptr[int(u)]:ptr[int(u) + 1]] = np.sort(np.fromiter(items, dtype=np.int64, count=len(items)))
+        self.ptr = torch.from_numpy(ptr).to(device)
+        self.items = torch.from_numpy(flat).to(device)
+        self.n_users, self.n_items, self.seed = int(n_users), int(n_items), int(seed)
+
+    def sample(self, user_ids: torch.Tensor, num_neg: int, epoch: int) -> torch.Tensor:
+        _need_cuda(user_ids, self.ptr)
+        user_ids = _i64c(user_ids.reshape(-1), "user_ids")
+        out = torch.empty((user_ids.numel(), int(num_neg)), dtype=torch.int64, device=user_ids.device)
+        _lib.check(_lib.load().b2r_sample_negatives(_p(user_ids), user_ids.numel(), int(num_neg), _p(self.ptr),
+                                                    _p(self.items), self.n_users, self.n_items,
+                                                    self.seed & 0xFFFFFFFFFFFFFFFF, int(epoch) & 0xFFFFFFFF, _p(out),
+                                                    _p(err_flag(user_ids.device)), _stream()), "b2r_sample_negatives")
+        return out
+
+
 def adam_exact_advance(W: torch.Tensor, m: torch.Tensor, v: torch.Tensor, last: torch.Tensor, upto: int, opt,
                        rows: Optional[torch.Tensor] = None, stamp: int = 0, state_ld: int = 0) -> None:
     """Groundwork for the exact dense-Adam mode (b2r_adam_exact_advance): bring the listed unique rows (all rows when

@@ -454,6 +454,15 @@ class GeneralModel(BaseModel):
                     "item_id": np.concatenate([[target], negs]).astype(int)}
 
         def actions_before_epoch(self):
+            sampler = self.model.__dict__.get("_b2r_device_sampler")
+            if sampler is not None:
+                # opt-in (runner --device_sampler 1; row f3 groundwork): same distribution drawn on the GPU from a
+                # counter-based stream keyed by (seed, epoch) instead of the Python rejection loop below
+                epoch = self.__dict__.get("_b2r_epoch", 0) + 1
+                self.__dict__["_b2r_epoch"] = epoch
+                users = torch.as_tensor(np.asarray(self.data["user_id"], dtype=np.int64)).to(self.model.device)
+                self.data["neg_items"] = sampler.sample(users, self.model.num_neg, epoch).cpu().numpy()
+                return
             # BaseModel.py:206-214: uniform negatives from NumPy's global RNG, rejected against train clicks
             n = len(self)
             neg = np.random.randint(1, self.corpus.n_items, size=(n, self.model.num_neg))

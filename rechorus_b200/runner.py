@@ -64,6 +64,9 @@ class BaseRunner:
         parser.add_argument("--exact_adam", type=int, default=0,
                             help="1 (with --fused_optimizer 1, Adam): row-sparse cost, dense torch.optim.Adam results "
                                  "(rows are advanced through their skipped steps; next-round groundwork)")
+        parser.add_argument("--device_sampler", type=int, default=0,
+                            help="non-zero seed: draw the training negatives on the GPU every epoch (same distribution "
+                                 "as BaseModel.py:206-214, counter-based stream; next-round groundwork)")
         parser.add_argument("--device_metrics", type=int, default=0,
                             help="1: rank the ground truth on the GPU (model.eval_ranks) instead of copying predictions "
                                  "to the host for evaluate_method")
@@ -104,6 +107,7 @@ class BaseRunner:
         self.device_metrics = getattr(args, "device_metrics", 0)
         self.fused_step = getattr(args, "fused_step", 0)
         self.exact_adam = getattr(args, "exact_adam", 0)
+        self.device_sampler = getattr(args, "device_sampler", 0)
         self.topk = [int(x) for x in args.topk.split(",")]
         self.metrics = [m.strip().upper() for m in args.metric.split(",")]
         self.main_metric = args.main_metric or f"{self.metrics[0]}@{self.topk[0]}"
@@ -196,6 +200,10 @@ class BaseRunner:
         model = dataset.model
         if model.optimizer is None:
             model.optimizer = self._build_optimizer(model)
+        if self.device_sampler and model.__dict__.get("_b2r_device_sampler") is None:
+            corpus = dataset.corpus
+            model.__dict__["_b2r_device_sampler"] = ops.DeviceNegativeSampler(
+                corpus.train_clicked_set, corpus.n_users, corpus.n_items, model.device, seed=self.device_sampler)
         dataset.actions_before_epoch()
         model.train()
         if self.fused_step and hasattr(model, "train_step") and isinstance(model.optimizer, RowSparseOptimizer):

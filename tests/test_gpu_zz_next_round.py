@@ -88,3 +88,52 @@ def test_exact_adam_mode_reproduces_dense_adam_training(l2):
     model.optimizer.flush()
     for k, v in model.state_dict().items():
         assert (v.cpu() - ref.p[k].detach()).abs().max() <= 2e-5, k
+
+
+def test_device_negative_sampler_equals_its_cpu_definition_bit_for_bit():
+    """integer work: the kernel's output must equal oracle.device_sampler_reference exactly; and it must have the
+    reference sampler's properties (range [1, n_items), never a training click of the row's user)"""
+    from oracle import rechorus_oracle as O
+    from rechorus_b200 import ops
+    rng = np.random.RandomState(3)
+    n_users, n_items, K = 37, 211, 6
+    clicked = {u: set(rng.randint(1, n_items, rng.randint(0, 60)).tolist()) for u in range(n_users)}
+    clicked[5] = set(range(1, n_items - 2))                 # almost everything clicked: long rejection chains
+    users = rng.randint(0, n_users, 500)
+    sampler = ops.DeviceNegativeSampler(clicked, n_users, n_items, torch.device("cuda", 0), seed=0x1234567890ABCDEF)
+    got = sampler.sample(torch.from_numpy(users).cuda(), K, epoch=3).cpu().numpy()
+    want = O.device_sampler_reference(users.tolist(), clicked, n_items, K, seed=0x1234567890ABCDEF, epoch=3)
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+    assert got.min() >= 1 and got.max() < n_items
+    for i, u in enumerate(users):
+        assert not (set(got[i].tolist()) & clicked[int(u)])
+    ops.check_ids()
+
+
+def test_runner_with_device_sampler_trains_on_valid_negatives():
+    import argparse
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import fit_corpus
+    from rechorus_b200 import plugin
+    from rechorus_b200.runner import BaseRunner
+    p = argparse.ArgumentParser()
+    p = BaseRunner.parse_runner_args(p)
+    p = plugin.BPRMF.parse_model_args(p)
+    a = p.parse_args(["--emb_size", "64", "--num_neg", "5", "--batch_size", "64", "--num_workers", "0", "--lr", "0.01",
+                      "--table_mode", "fused", "--fused_optimizer", "1", "--fused_step", "1", "--device_sampler", "77"])
+    a.device, a.model_path, a.log_file = torch.device("cuda", 0), "/tmp/_b2r_ds.pt", ""
+    corpus = fit_corpus.build()
+    torch.manual_seed(1)
+    model = plugin.BPRMF(a, corpus).to(a.device)
+    train = plugin.BPRMF.Dataset(model, corpus, "train")
+    runner = BaseRunner(a)
+    l1 = runner.fit(train, epoch=1)
+    neg1 = np.array(train.data["neg_items"])
+    l2 = runner.fit(train, epoch=2)
+    neg2 = np.array(train.data["neg_items"])
+    assert np.isfinite(l1) and np.isfinite(l2)
+    assert neg1.shape == (len(train), 5) and neg1.min() >= 1 and neg1.max() < corpus.n_items
+    assert not np.array_equal(neg1, neg2)                   # a fresh draw every epoch
+    for i, u in enumerate(train.data["user_id"]):
+        assert not (set(neg1[i].tolist()) & corpus.train_clicked_set[u])

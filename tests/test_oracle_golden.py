@@ -100,3 +100,29 @@ def test_lazy_exact_adam_equals_dense_adam(wd):
         lazy.step(rows, g)
     lazy.flush()
     assert (lazy.W - dense.detach()).abs().max() <= 1e-12
+
+
+def test_philox_known_answers_and_sampler_reference_properties():
+    """Random123's known-answer vectors for Philox4x32-10 pin the generator the device sampler is defined on; the
+    sampler reference has the reference's distribution properties (range, clicked-set rejection, determinism)."""
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert O.philox4x32_10(ctr, key) == want
+    n_items = 40
+    clicked = {u: set(range(1 + u, n_items, 3)) for u in range(5)}          # a third of the catalogue each
+    users = [0, 1, 2, 3, 4] * 200
+    neg = O.device_sampler_reference(users, clicked, n_items, 4, seed=7, epoch=1)
+    assert neg.min() >= 1 and neg.max() < n_items
+    for i, u in enumerate(users):
+        assert not (set(neg[i].tolist()) & clicked[u])
+    assert np.array_equal(neg, O.device_sampler_reference(users, clicked, n_items, 4, seed=7, epoch=1))
+    assert not np.array_equal(neg, O.device_sampler_reference(users, clicked, n_items, 4, seed=7, epoch=2))
+    # uniform over the allowed items of user 0: 1000 x 4 / 5 = 800 draws over 26 items
+    draws = neg[0::5].reshape(-1)
+    allowed = sorted(set(range(1, n_items)) - clicked[0])
+    counts = np.array([(draws == a).sum() for a in allowed])
+    expected = len(draws) / len(allowed)
+    assert ((counts - expected) ** 2 / expected).sum() < 2.5 * len(allowed)   # chi-square, generous bound
