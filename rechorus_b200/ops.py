@@ -13,6 +13,8 @@ Embedding-table gradients can leave the autograd graph in three forms, selected 
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -694,6 +696,11 @@ def linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, y_relu: Optio
     return dx, dW, db
 
 
+# opt-in: run every Linear forward of the dense models on the tcgen05 kernel (verified to fp32-class accuracy in
+# tests/test_gpu_tc.py, currently ~10 % slower than the SGEMM at K = 64 -- DESIGN.md §6); off unless B2R_TC_LINEAR=1
+_TC_LINEAR = os.environ.get("B2R_TC_LINEAR") == "1"
+
+
 class _Linear(torch.autograd.Function):
     """nn.Linear (+ optional ReLU) on the library's SGEMM: NeuMF.py:70 / layers.py:26-28,106-107."""
 
@@ -703,7 +710,11 @@ class _Linear(torch.autograd.Function):
         x2 = x.reshape(-1, shape[-1])
         if x2.stride(1) != 1:
             x2 = x2.contiguous()
-        y = linear_fwd(x2, W, bias, relu)
+        N, K = W.shape
+        if _TC_LINEAR and K % 32 == 0 and K <= 128 and N % 16 == 0 and N <= 256:
+            y = linear_fwd_tc(x2, W, bias, relu)          # tcgen05 TF32-split forward (opt-in, B2R_TC_LINEAR=1)
+        else:
+            y = linear_fwd(x2, W, bias, relu)
         ctx.save_for_backward(x2, W, y if relu else None)
         ctx.has_bias, ctx.shape = bias is not None, shape
         return y.view(*shape[:-1], W.shape[0])

@@ -29,3 +29,7 @@ for SC in 2 4 8; do for PC in 4 8; do
   B2R_SORT_CAP=$SC B2R_PART_CAP=$PC timeout 300 python bench.py --steps 600 --warmup 20 --no_cpu_baseline 2>/dev/null | tail -1 | python -c "
 import sys,json; d=json.loads(sys.stdin.read()); print('sort_cap $SC part_cap $PC: ms %.4f apply %.4f plan %.4f fused %.4f'%(d['ms_per_step'], d['roofline']['kernel_ms'], d['kernels']['plan_items']['ms'], d['kernels']['fused_score_loss_bwd']['ms']))"
 done; done
+# SASRec / NeuMF with every Linear forward on the tcgen05 kernel: parity, step time, tensor-pipe activity
+B2R_TC_LINEAR=1 timeout 600 python -m pytest tests/test_gpu_models.py tests/test_gpu_dense.py -x -q > gpurun_out/n_pytest_tc.log 2>&1; echo "B2R_TC_LINEAR=1 pytest rc=$? $(tail -1 gpurun_out/n_pytest_tc.log)"
+B2R_TC_LINEAR=1 timeout 400 python tools/model_bench.py 2>/dev/null | grep -E '^\{' | cut -c1-200
+timeout 400 ncu --metrics gpu__time_duration.sum,sm__inst_executed_pipe_tensor.sum,sm__pipe_tensor_op_umma_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_linear_fwd_tc -c 6 --csv --log-file gpurun_out/n_tc_pipe.csv env B2R_TC_LINEAR=1 python tools/model_bench.py > /dev/null 2>&1; tail -8 gpurun_out/n_tc_pipe.csv | cut -d, -f5,13-
