@@ -174,7 +174,8 @@ def run_ours(args, rank, world, local_rank):
     ops.check_ids(device)
     tags = {"score_fwd": L.PROF_SCORE_FWD, "score_bwd_query": L.PROF_SCORE_BWDQ, "segment_adam_items": L.PROF_SEGMENT_I,
             "segment_adam_users": L.PROF_SEGMENT_U, "plan_items": L.PROF_PLAN_I, "loss": L.PROF_LOSS}
-    prof_every = max(1, args.steps // 64)            # bracket the tagged kernels on every prof_every-th step
+    prof_every = max(16, args.steps // 64)           # bracket the tagged kernels on every prof_every-th step (>= 1 sample;
+                                                      # sparse, so the brackets' events do not weigh on a short timed run)
     prof_steps = list(range(0, args.steps, prof_every))
     evs = {name: {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                   for k in prof_steps} for name in tags}
