@@ -42,6 +42,8 @@ def test_bprmf_two_epochs_equal_reference_runner():
             assert abs(metrics[k[2:]] - float(gold[k])) <= 1.0 / 48 + 1e-9, (k, metrics[k[2:]], float(gold[k]))
 
 
+@pytest.mark.skipif(os.environ.get("B2R_NEXT") is None,
+                    reason="written after this round's GPU budget was spent: first run is tools/gpu_next_round.sh")
 @pytest.mark.parametrize("case", ["fit_neumf", "fit_sasrec"])
 def test_deep_models_two_epochs_track_reference_runner(case):
     name = fit_corpus.CASES[case][0]

@@ -3,7 +3,7 @@
 #   B2R_NEXT bit 0 = counting-sort k_bucket_sort, bit 1 = warp-per-sample fused kernel (d=64, C<=104).
 # For each setting: the parity tests that exercise the changed kernel, then the bench line; then ncu times alone.
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_zz_fit_golden.py -q > gpurun_out/n_pytest_zz.log 2>&1; echo "zz tests (default kernels) rc=$?"; tail -3 gpurun_out/n_pytest_zz.log
+B2R_NEXT=0 timeout 600 python -m pytest tests/test_gpu_zz_fit_golden.py -q > gpurun_out/n_pytest_zz.log 2>&1; echo "zz tests (default kernels) rc=$?"; tail -3 gpurun_out/n_pytest_zz.log
 B2R_NEXT=0 timeout 300 python -m pytest tests/test_gpu_zz_next_round.py -q > gpurun_out/n_pytest_next.log 2>&1; echo "next-round groundwork tests rc=$?"; tail -3 gpurun_out/n_pytest_next.log
 for NX in 0 1 2 3; do
   B2R_NEXT=$NX timeout 600 python -m pytest tests/test_gpu_bprmf.py tests/test_gpu_fullsize.py tests/test_gpu_shard.py tests/test_gpu_runner_fit.py -x -q > gpurun_out/n_pytest_$NX.log 2>&1
