@@ -92,3 +92,44 @@ def test_whole_step_fit_equals_autograd_fit_under_sgd():
     assert np.allclose(out["nodes"][0], out["steps"][0], rtol=2e-5, atol=2e-5), (out["nodes"][0], out["steps"][0])
     for k, v in out["nodes"][1].items():
         assert (v - out["steps"][1][k]).abs().max() <= 2e-6, k
+
+
+def test_eval_ranks_test_all_equal_reference_predict_fixture():
+    """the plugin's device route for --test_all 1 (b2r_rank_all_items + clicked-item masking, scores never
+    materialised) gives the integer ranks of the REFERENCE's own BaseRunner.predict + evaluate_method
+    (tests/golden/eval_test_all.npz, made by tests/golden/make_eval_golden.py)"""
+    import argparse
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    import fit_corpus
+    from rechorus_b200 import ops, plugin
+    from rechorus_b200.runner import BaseRunner
+    gold = np.load(os.path.join(golden, "eval_test_all.npz"))
+    p = argparse.ArgumentParser()
+    p = BaseRunner.parse_runner_args(p)
+    p = plugin.BPRMF.parse_model_args(p)
+    a = p.parse_args(["--emb_size", "64", "--test_all", "1", "--device_metrics", "1"] + fit_corpus.COMMON)
+    a.device, a.model_path, a.log_file = torch.device("cuda", 0), "/tmp/_b2r_evalg.pt", ""
+    corpus = fit_corpus.build()
+    model = plugin.BPRMF(a, corpus)
+    model.load_state_dict({k[2:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w:")})
+    model = model.to(a.device)
+    dev = plugin.BPRMF.Dataset(model, corpus, "dev")
+    dev.prepare()
+    runner = BaseRunner(a)
+    metrics = runner.evaluate(dev, [5, 10, 20], ["HR", "NDCG"])          # device route
+    for k in gold.files:
+        if k.startswith("m:"):
+            assert abs(metrics[k[2:]] - float(gold[k])) <= 1e-12, (k, metrics[k[2:]], float(gold[k]))
+    # and the ranks themselves, batch by batch
+    batch = dev.collate_batch([dev[i] for i in range(len(dev))])
+    uids = dev.data["user_id"]
+    rows = torch.tensor([i for i, u in enumerate(uids) for _ in (corpus.train_clicked_set[u] | corpus.residual_clicked_set[u])])
+    cols = torch.tensor([j for u in uids for j in (corpus.train_clicked_set[u] | corpus.residual_clicked_set[u])])
+    feed = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+    model.eval()
+    ranks = model.eval_ranks(feed, rows.cuda(), cols.cuda()).cpu().numpy()
+    assert np.array_equal(ranks, gold["gt_rank"])
+    ops.check_ids()

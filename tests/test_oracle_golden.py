@@ -126,3 +126,30 @@ def test_philox_known_answers_and_sampler_reference_properties():
     counts = np.array([(draws == a).sum() for a in allowed])
     expected = len(draws) / len(allowed)
     assert ((counts - expected) ** 2 / expected).sum() < 2.5 * len(allowed)   # chi-square, generous bound
+
+
+def test_test_all_protocol_matches_reference_predict_fixture():
+    """tests/golden/eval_test_all.npz = the reference's own BaseRunner.predict under --test_all 1 (candidate list,
+    BPRMF scores, clicked-item masking): the oracle's restatement reproduces the masked predictions, the integer ranks
+    and the metrics"""
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    import fit_corpus
+    gold = np.load(os.path.join(golden, "eval_test_all.npz"))
+    corpus = fit_corpus.build()
+    U, I = torch.from_numpy(gold["w:u_embeddings.weight"]), torch.from_numpy(gold["w:i_embeddings.weight"])
+    uid, target = torch.from_numpy(gold["user_id"]), torch.from_numpy(gold["item_id"])
+    clicked = [corpus.train_clicked_set[int(u)] | corpus.residual_clicked_set[int(u)] for u in uid]
+    pred = O.test_all_predictions(U[uid], I, target, clicked)
+    ref = gold["pred"]
+    assert pred.shape == ref.shape
+    assert np.array_equal(np.isneginf(pred), np.isneginf(ref))
+    finite = np.isfinite(ref)
+    assert np.abs(pred[finite] - ref[finite]).max() <= 1e-5
+    assert np.array_equal(O.gt_rank(pred), gold["gt_rank"])
+    m = O.rank_metrics(pred, [5, 10, 20], ["HR", "NDCG"])
+    for k in gold.files:
+        if k.startswith("m:"):
+            assert abs(m[k[2:]] - float(gold[k])) <= 1e-12
