@@ -261,6 +261,17 @@ B2R_API int b2r_attention_fwd(const float* q, const float* k, const float* v, in
                       int H, b2r_stream_t stream);
 B2R_API int b2r_attention_bwd(const float* q, const float* k, const float* v, int ld, const float* dctx, float* dq,
                       float* dk, float* dv, int ldg, int B, int L, int d, int H, b2r_stream_t stream);
+/* Groundwork, opt-in (B2R_SASREC_LASTQ=1), not used by the default paths of this round: attention for ONE query per
+ * sequence -- the query at position t* = clamp(lengths[b]-1, 0, L-1), the only position of SASRec's last block whose
+ * output is used (models/sequential/SASRec.py:74-81) -- against keys/values 0..t* (the causal row of
+ * utils/layers.py:52-63).  q_last, ctx_last, dq_last are [B, d]; k, v, dk, dv are [B, L, d] rows with leading
+ * dimension ld / ldg; prob [B, H, L] keeps the softmax row for the backward.  Identical results to b2r_attention_fwd/
+ * bwd restricted to that query; rows of dk, dv beyond t* are written as zeros. */
+B2R_API int b2r_attention_last_fwd(const float* q_last, const float* k, const float* v, int ld, const int64_t* lengths,
+                                   float* ctx_last, float* prob, int B, int L, int d, int H, b2r_stream_t stream);
+B2R_API int b2r_attention_last_bwd(const float* q_last, const float* k, const float* v, int ld, const int64_t* lengths,
+                                   const float* prob, const float* dctx_last, float* dq_last, float* dk, float* dv,
+                                   int ldg, int B, int L, int d, int H, b2r_stream_t stream);
 B2R_API int b2r_select_last(const float* y, const int64_t* hist, const int64_t* lengths, float* h, int B, int L,
                     int d, b2r_stream_t stream);
 B2R_API int b2r_select_last_bwd(const float* dh, const int64_t* hist, const int64_t* lengths, float* dy, int B, int L,

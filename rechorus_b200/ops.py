@@ -805,6 +805,40 @@ def causal_attention(q, k, v, num_heads):
     return _CausalAttention.apply(q, k, v, num_heads)
 
 
+class _AttentionLast(torch.autograd.Function):
+    """Attention for the one query per sequence that SASRec's last block needs (position len-1): q_last [B, d] against
+    k, v [B, L, d]; identical to row len-1 of _CausalAttention.  Opt-in groundwork (B2R_SASREC_LASTQ=1)."""
+
+    @staticmethod
+    def forward(ctx, q_last, k, v, lengths, H):
+        _need_cuda(q_last, k, v, lengths)
+        B, Ln, d = k.shape
+        q_last, k, v = _f32c(q_last, "q_last"), _f32c(k, "k"), _f32c(v, "v")
+        lengths = _i64c(lengths, "lengths")
+        out = torch.empty((B, d), dtype=torch.float32, device=k.device)
+        prob = torch.empty((B, H, Ln), dtype=torch.float32, device=k.device)
+        _lib.check(_lib.load().b2r_attention_last_fwd(_p(q_last), _p(k), _p(v), d, _p(lengths), _p(out), _p(prob), B, Ln,
+                                                      d, H, _stream()), "b2r_attention_last_fwd")
+        ctx.save_for_backward(q_last, k, v, lengths, prob)
+        ctx.H = H
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q_last, k, v, lengths, prob = ctx.saved_tensors
+        B, Ln, d = k.shape
+        dout = _f32c(dout, "dctx_last")
+        dq, dk, dv = torch.empty_like(q_last), torch.empty_like(k), torch.empty_like(k)
+        _lib.check(_lib.load().b2r_attention_last_bwd(_p(q_last), _p(k), _p(v), d, _p(lengths), _p(prob), _p(dout), _p(dq),
+                                                      _p(dk), _p(dv), d, B, Ln, d, ctx.H, _stream()),
+                   "b2r_attention_last_bwd")
+        return dq, dk, dv, None, None
+
+
+def attention_last(q_last, k, v, lengths, num_heads):
+    return _AttentionLast.apply(q_last, k, v, lengths, num_heads)
+
+
 class _EmbedHistory(torch.autograd.Function):
     """x = I[hist] + P[(len - t) * valid]  (SASRec.py:58-66); backward: row-sparse scatter into I (padding
     positions dropped: their gradient is exactly zero) and the dense small-table gradient of P."""

@@ -32,6 +32,10 @@ from . import ops
 # ======================================================================================================
 
 
+# opt-in groundwork for the next round (not yet run on a GPU): SASRec's last block for one query per sequence
+_SASREC_LASTQ = os.environ.get("B2R_SASREC_LASTQ") == "1"
+
+
 class _KernelModelMixin:
     """Shared by every kernel-backed model: table registry + loss + optional inference hook."""
 
@@ -280,10 +284,31 @@ class SASRecKernels(_KernelModelMixin):
         self.transformer_block = nn.ModuleList(
             [_TransformerParams(self.emb_size, self.emb_size) for _ in range(self.num_layers)])
 
+    def _last_block_one_query(self, blk, x, history, lengths):
+        """The last block for the only position whose output SASRec uses (len-1, SASRec.py:74-81): keys and values from
+        every position, query / residual LayerNorms / FFN for that one row per sequence.  Same result as the full block
+        followed by select_last; opt-in groundwork (B2R_SASREC_LASTQ=1), dropout-free path only."""
+        a = blk.masked_attn_head
+        ones = torch.ones_like(history)
+        x_last = ops.select_last(x, ones, lengths)                               # raw row len-1 (no padding mask yet)
+        q_last = ops.linear(x_last, a.q_linear.weight, a.q_linear.bias)
+        k = ops.linear(x, a.k_linear.weight, a.k_linear.bias)
+        v = ops.linear(x, a.v_linear.weight, a.v_linear.bias)
+        ctx_last = ops.attention_last(q_last, k, v, lengths, self.num_heads)
+        c = ops.add_layernorm(ctx_last, x_last, blk.layer_norm1.weight, blk.layer_norm1.bias)
+        o = ops.linear(ops.linear(c, blk.linear1.weight, blk.linear1.bias, relu=True), blk.linear2.weight, blk.linear2.bias)
+        y = ops.add_layernorm(o, c, blk.layer_norm2.weight, blk.layer_norm2.bias)  # [B, d]
+        t_last = (lengths - 1).clamp(0, history.shape[1] - 1)
+        valid = (history.gather(1, t_last.view(-1, 1)) > 0).to(y.dtype)            # SASRec.py:74: y * valid_his
+        return y * valid
+
     def user_state(self, history, lengths):
         x = ops.embed_history(self.i_embeddings.weight, self.p_embeddings.weight, history, lengths)   # [B, L, d]
         p = self.dropout
-        for blk in self.transformer_block:
+        n_blocks = len(self.transformer_block)
+        for bi, blk in enumerate(self.transformer_block):
+            if _SASREC_LASTQ and bi == n_blocks - 1 and not (p > 0):
+                return self._last_block_one_query(blk, x, history, lengths)
             a = blk.masked_attn_head
             q = ops.linear(x, a.q_linear.weight, a.q_linear.bias)
             k = ops.linear(x, a.k_linear.weight, a.k_linear.bias)
