@@ -34,5 +34,5 @@ B2R_TC_LINEAR=1 timeout 600 python -m pytest tests/test_gpu_models.py tests/test
 B2R_TC_LINEAR=1 timeout 400 python tools/model_bench.py 2>/dev/null | grep -E '^\{' | cut -c1-200
 timeout 400 ncu --metrics gpu__time_duration.sum,sm__inst_executed_pipe_tensor.sum,sm__pipe_tensor_op_umma_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_linear_fwd_tc -c 6 --csv --log-file gpurun_out/n_tc_pipe.csv env B2R_TC_LINEAR=1 python tools/model_bench.py > /dev/null 2>&1; tail -8 gpurun_out/n_tc_pipe.csv | cut -d, -f5,13-
 # SASRec with the last block computed for one query per sequence (exact): parity on the fixtures, step time
-B2R_SASREC_LASTQ=1 timeout 600 python -m pytest tests/test_gpu_models.py tests/test_gpu_fullsize.py -x -q -k "sasrec or SASRec or config4 or c4" > gpurun_out/n_pytest_lastq.log 2>&1; echo "B2R_SASREC_LASTQ=1 pytest rc=$? $(tail -1 gpurun_out/n_pytest_lastq.log)"
+B2R_SASREC_LASTQ=1 timeout 600 python -m pytest tests/test_gpu_models.py tests/test_gpu_fullsize.py -x -q > gpurun_out/n_pytest_lastq.log 2>&1; echo "B2R_SASREC_LASTQ=1 pytest rc=$? $(tail -1 gpurun_out/n_pytest_lastq.log)"
 B2R_SASREC_LASTQ=1 timeout 400 python tools/model_bench.py 2>/dev/null | grep -E '^\{' | grep -i sasrec | cut -c1-200
