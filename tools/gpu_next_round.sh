@@ -36,3 +36,8 @@ timeout 400 ncu --metrics gpu__time_duration.sum,sm__inst_executed_pipe_tensor.s
 # SASRec with the last block computed for one query per sequence (exact): parity on the fixtures, step time
 B2R_SASREC_LASTQ=1 timeout 600 python -m pytest tests/test_gpu_models.py tests/test_gpu_fullsize.py -x -q > gpurun_out/n_pytest_lastq.log 2>&1; echo "B2R_SASREC_LASTQ=1 pytest rc=$? $(tail -1 gpurun_out/n_pytest_lastq.log)"
 B2R_SASREC_LASTQ=1 timeout 400 python tools/model_bench.py 2>/dev/null | grep -E '^\{' | grep -i sasrec | cut -c1-200
+# where the next batch's plan overlaps: from the step's start (default) or only after the forward kernel
+for PA in 0 1; do
+  B2R_PLAN_AFTER=$PA timeout 300 python bench.py --steps 1000 --warmup 20 --no_cpu_baseline 2>/dev/null | tail -1 | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print('plan_after $PA: ms %.4f e2e %.4f apply %.4f plan %.4f fused %.4f'%(d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['kernel_ms'], d['kernels']['plan_items']['ms'], d['kernels']['fused_score_loss_bwd']['ms']))"
+done
