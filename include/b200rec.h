@@ -88,6 +88,14 @@ B2R_API int b2r_gather_rows_strided(const float* T, const int64_t* ids, int64_t 
 B2R_API int b2r_pairdot_fwd(const float* Q, const int64_t* qidx, int64_t n_q, const float* T, const int64_t* rows,
                     int64_t n_t, float* out, int64_t n, int d, int32_t* err_flag, b2r_stream_t stream);
 
+/* Groundwork, opt-in (B2R_SHARD_P2P=1), not used by the default paths of this round: b2r_pairdot_fwd whose result for
+ * pair e is stored at out_tab[e / seg][e % seg] -- out_tab is a DEVICE array of n / seg pointers, typically the
+ * peer-mapped receive buffers of the ranks the pairs came from (torch.distributed._symmetric_memory), so the scores
+ * reach their requesters by NVLink stores from inside the kernel instead of an all-to-all. */
+B2R_API int b2r_pairdot_fwd_p2p(const float* Q, const int64_t* qidx, int64_t n_q, const float* T, const int64_t* rows,
+                                int64_t n_t, float* const* out_tab, int64_t seg, int64_t n, int d, int32_t* err_flag,
+                                b2r_stream_t stream);
+
 /* out[key[e],:] = sum over each run of consecutive valid pairs sharing key[e] of coef[e] * T[rows[e],:]  (rows < 0 =
  * unused slot; every key occupies one contiguous run, as the stable owner-bucketing of the sharded exchange
  * guarantees; out rows without pairs are left untouched).  The shard owner's half of dQ = sum_c g * I[id]. */

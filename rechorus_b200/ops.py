@@ -141,6 +141,22 @@ def pairdot(Q: torch.Tensor, qidx: torch.Tensor, T: torch.Tensor, rows: torch.Te
     return out
 
 
+def pairdot_p2p(Q: torch.Tensor, qidx: torch.Tensor, T: torch.Tensor, rows: torch.Tensor, out_tab: torch.Tensor,
+                seg: int) -> None:
+    """pairdot whose score for pair e goes to out_tab[e // seg][e % seg]; out_tab: int64 device tensor of float*
+    addresses (peer-mapped receive buffers).  Opt-in groundwork for the fused exchange of config 5 (b2r_pairdot_fwd_p2p)."""
+    _need_cuda(Q, qidx, T, rows, out_tab)
+    Q, T = _f32c(Q, "Q"), _f32c(T, "T")
+    qidx, rows = _i64c(qidx.reshape(-1), "qidx"), _i64c(rows.reshape(-1), "rows")
+    out_tab = _i64c(out_tab, "out_tab")
+    n = rows.numel()
+    if n != out_tab.numel() * int(seg):
+        raise ValueError("pairdot_p2p: n must equal len(out_tab) * seg")
+    _lib.check(_lib.load().b2r_pairdot_fwd_p2p(_p(Q), _p(qidx), Q.shape[0], _p(T), _p(rows), T.shape[0], _p(out_tab),
+                                               int(seg), n, T.shape[1], _p(err_flag(Q.device)), _stream()),
+               "b2r_pairdot_fwd_p2p")
+
+
 def pair_runs_sum(out: torch.Tensor, key: torch.Tensor, rows: torch.Tensor, coef: torch.Tensor, T: torch.Tensor) -> None:
     """out[key[e]] = sum over each contiguous run of valid pairs with that key of coef[e] * T[rows[e]]
     (b2r_pair_runs_sum; rows < 0 = unused slot)"""

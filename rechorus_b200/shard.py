@@ -31,6 +31,7 @@ CPU stand-in to exercise the exchange bookkeeping under gloo.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -47,6 +48,10 @@ class CudaBackend:
     def pairdot(self, Q, qidx, T, rows):
         from . import ops
         return ops.pairdot(Q, qidx, T, rows)
+
+    def pairdot_p2p(self, Q, qidx, T, rows, out_tab, seg):
+        from . import ops
+        ops.pairdot_p2p(Q, qidx, T, rows, out_tab, seg)
 
     def bpr_loss_and_grad(self, pred):
         from . import ops
@@ -115,6 +120,31 @@ class ShardedBPRMF:
             if optimizer != "SGD":
                 st["v"] = torch.zeros_like(W)
 
+    # -- opt-in groundwork (B2R_SHARD_P2P=1, not yet run on a GPU): scores returned by peer stores ----------
+    def _peer_scores(self, cap: int):
+        """Symmetric [W, cap] float32 score buffer + the device table of peer pointers this rank writes through
+        (entry s = rank s's buffer, row `my rank`).  Returns None when the feature is off or cannot be set up -- the
+        caller then uses the NCCL all-to-all."""
+        if not (os.environ.get("B2R_SHARD_P2P") == "1" and self.world > 1 and self.U.is_cuda):
+            return None
+        cache = self.__dict__.setdefault("_p2p_cache", {})
+        if cap in cache:
+            return cache[cap]
+        try:
+            import torch.distributed._symmetric_memory as symm
+            W = self.world
+            buf = symm.empty(W * cap, dtype=torch.float32, device=self.U.device)
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            me = dist.get_rank(self.group)
+            ptrs = [int(hdl.buffer_ptrs[s]) + me * cap * 4 for s in range(W)]
+            tab = torch.tensor(ptrs, dtype=torch.int64, device=self.U.device)
+            cache[cap] = (hdl, buf.view(W, cap), tab)
+        except Exception as e:                                # pragma: no cover - depends on the box
+            import warnings
+            warnings.warn(f"B2R_SHARD_P2P: symmetric memory unavailable ({e!r}); using the NCCL exchange")
+            cache[cap] = None
+        return cache[cap]
+
     # -- collectives (degenerate to copies for a single rank) --------------------------------------------
     def _a2a(self, x: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
@@ -178,7 +208,18 @@ class ShardedBPRMF:
         qidx = (recv_pairs & ((1 << 21) - 1)) + src_base                          # row of q_all (garbage where rows < 0)
         qidx = torch.where(rows >= 0, qidx, torch.zeros_like(qidx))
         # D. owners score, scores travel back
-        sc_recv = self._a2a(be.pairdot(q_all, qidx, self.I, rows).view(W, cap))   # [W(owner), cap]
+        p2p = self._peer_scores(cap)
+        if p2p is None:
+            sc_recv = self._a2a(be.pairdot(q_all, qidx, self.I, rows).view(W, cap))   # [W(owner), cap]
+        else:
+            # fused compute + exchange: the owner's scoring kernel stores each score into the requester's buffer over
+            # NVLink; the barriers order those stores against the requester's reads (before: nobody still reads the
+            # previous step's scores; after: every owner's stores have landed)
+            hdl, local, tab = p2p
+            hdl.barrier(channel=0)
+            be.pairdot_p2p(q_all, qidx, self.I, rows, tab, cap)
+            hdl.barrier(channel=1)
+            sc_recv = local                                                          # [W(owner), cap]
         pred = torch.empty(n, dtype=torch.float32, device=dev)
         pred[ord_i] = sc_recv[own_is, keep_rank]
         state = dict(B=B, C=C, n=n, cap=cap, ord_u=ord_u, own_us=own_us, rank_u=rank_u, recv_uid=recv_uid,

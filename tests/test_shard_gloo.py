@@ -86,7 +86,8 @@ def _worker(rank, world, port, out_q):
     for uid, iid in _batches(rank):
         pred, _ = m.scores(uid, iid)
         losses.append(float(m.train_step(uid, iid)))
-    out_q.put((rank, m.U.clone(), m.I.clone(), losses, pred.clone()))
+    # by value (numpy), not as shared-memory tensors: the parent may unpickle after this process has exited
+    out_q.put((rank, m.U.numpy().copy(), m.I.numpy().copy(), losses, pred.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -102,7 +103,7 @@ def test_sharded_step_equals_single_process_oracle(world):
     got = {}
     for _ in range(world):
         r, U, I, losses, pred = q.get(timeout=240)
-        got[r] = (U, I, losses, pred)
+        got[r] = (torch.from_numpy(U), torch.from_numpy(I), losses, torch.from_numpy(pred))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
