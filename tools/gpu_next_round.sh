@@ -41,3 +41,5 @@ for PA in 0 1; do
   B2R_PLAN_AFTER=$PA timeout 300 python bench.py --steps 1000 --warmup 20 --no_cpu_baseline 2>/dev/null | tail -1 | python -c "
 import sys,json; d=json.loads(sys.stdin.read()); print('plan_after $PA: ms %.4f e2e %.4f apply %.4f plan %.4f fused %.4f'%(d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['kernel_ms'], d['kernels']['plan_items']['ms'], d['kernels']['fused_score_loss_bwd']['ms']))"
 done
+# Multi-GPU candidate (separate call, charged 2x):  gpurun --gpus 2 -- 'B2R_SHARD_P2P=1 bash tools/gpu_shard.sh 2 nobench'
+# -> the --check line must stay <= 1e-5 / update_ok, then compare the c5 ms_per_step with the NCCL-only run.
