@@ -375,6 +375,9 @@ B2R_API size_t b2r_bprmf_step_workspace_bytes(int B, int C, int d, int64_t n_use
 B2R_API int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t n_users, int64_t n_items, void* ws,
                          size_t ws_bytes);
 B2R_API int b2r_bprmf_ctx_destroy(void* ctx);
+/* forget the prefetched plan (call at the start of an epoch and after an aborted one): a prefetched plan is matched to
+ * the next batch by its id pointers, which a caching allocator may hand out again for a different batch */
+B2R_API int b2r_bprmf_ctx_reset(void* ctx);
 B2R_API int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const int64_t* uid, const int64_t* iid,
                          const int64_t* next_uid, const int64_t* next_iid, const b2r_optim* opt,
                          float* loss_out, int32_t* err_flag, b2r_stream_t stream);

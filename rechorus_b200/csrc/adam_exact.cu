@@ -1,6 +1,6 @@
 // adam_exact.cu -- groundwork for the exact dense-Adam mode of the row-sparse optimizer (DESIGN.md §8 item 2;
 // reference semantics: torch.optim.Adam built by helpers/BaseRunner.py:110-114, applied to the whole table at :206).
-// NOT used by any default path of this round and not yet run on a GPU.
+// Opt-in (--exact_adam 1); not part of the default row-sparse (lazy) path.
 //
 // Dense Adam keeps moving a row it has no gradient for: m <- b1 m, v <- b2 v (plus the g = wd * w terms under weight
 // decay) and w <- w - lr * m_hat / (sqrt(v_hat) + eps) at every step.  A row-sparse table reproduces that if every
@@ -35,18 +35,23 @@ k_adam_exact_advance(const int64_t* __restrict__ rows, int64_t n, int64_t n_rows
             if (err_flag && sub == 0) atomicAdd(err_flag, 1);
             continue;
         }
-        const int t0 = last[row];
-        if (t0 >= upto) {                                  // already there (all lanes of the group agree)
+        // lane 0 of the group reads the stamp and broadcasts it: the same lane re-stamps the row at the end of the
+        // iteration, so no other lane may read last[row] itself (a lagging lane could see the new stamp and skip)
+        const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
+        int t0 = (sub == 0) ? last[row] : 0;
+        t0 = __shfl_sync(gmask, t0, 0, LPR);
+        if (t0 >= upto) {                                  // already there (group-uniform)
             if (sub == 0 && stamp > t0) last[row] = stamp;
             continue;
         }
         float4 w = ld4(W + row * D + sub * 4);
         float4 m = ld4(M + row * sld + sub * 4);
         float4 v = ld4(V + row * sld + sub * 4);
+        // per lane: a slice whose moments are all zero (and no weight decay) does not move under dense Adam either;
+        // slices are elementwise independent, so lanes may decide this on their own
         const bool still = (k.wd == 0.f) && m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f &&
                            v.y == 0.f && v.z == 0.f && v.w == 0.f;
-        // a row is "still" only if every lane's slice is: the loop trip count must not depend on the lane anyway
-        if (!still || k.wd != 0.f) {
+        if (!still) {
             float p1 = exp2f(k.log2b1 * (float)t0), p2 = exp2f(k.log2b2 * (float)t0);
             float* wp = &w.x;
             float* mp = &m.x;
@@ -69,6 +74,7 @@ k_adam_exact_advance(const int64_t* __restrict__ rows, int64_t n, int64_t n_rows
             st4(M + row * sld + sub * 4, m);
             st4(V + row * sld + sub * 4, v);
         }
+        __syncwarp(gmask);
         if (sub == 0) last[row] = stamp > upto ? stamp : upto;
     }
 }

@@ -149,6 +149,14 @@ extern "C" int b2r_bprmf_ctx_destroy(void* ctx) {
     return 0;
 }
 
+extern "C" int b2r_bprmf_ctx_reset(void* ctx) {
+    if (!ctx) return 0;
+    StepCtx* c = static_cast<StepCtx*>(ctx);
+    c->have_pre = false;
+    c->pre_uid = c->pre_iid = nullptr;
+    return 0;
+}
+
 static int build_plans(StepCtx* c, int slot, const int64_t* uid, const int64_t* iid, int32_t* err_flag) {
     char* base = c->ws;
     const PlanBuf& p = c->L.plan[slot];

@@ -72,7 +72,7 @@ k_target_score(const float* __restrict__ Q, int ldq, const float* __restrict__ I
     if (b >= B) return;
     int64_t t = target[b];
     if (t < 0 || t >= n_items) {
-        if (err_flag) atomicExch(err_flag, 1);
+        if (err_flag) atomicAdd(err_flag, 1);
         t = 0;
     }
     const float* q = Q + (int64_t)b * ldq;
@@ -179,7 +179,7 @@ k_rank_unmask(const float* __restrict__ Q, int ldq, const float* __restrict__ I,
     for (int64_t e = (int64_t)blockIdx.x * kRT + threadIdx.x; e < E; e += (int64_t)gridDim.x * kRT) {
         const int64_t b = mask_row[e], j = mask_item[e];
         if (b < 0 || b >= B) {
-            if (err_flag) atomicExch(err_flag, 1);
+            if (err_flag) atomicAdd(err_flag, 1);
             continue;
         }
         if (j < 1 || j >= n_items) continue;       // not a column of the candidate list

@@ -130,6 +130,7 @@ SIGNATURES = {
     "b2r_bprmf_ctx_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                        C.c_void_p, C.c_size_t]),
     "b2r_bprmf_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "b2r_bprmf_ctx_reset": (C.c_int, [C.c_void_p]),
     "b2r_bprmf_train_step": (C.c_int, [C.c_void_p, C.POINTER(BprmfTables), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.POINTER(Optim), C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -76,6 +76,13 @@ def check_ids(device: Optional[torch.device] = None) -> None:
         raise IndexError(f"{bad} embedding id(s) out of range (kernels clamped them to row 0)")
 
 
+def poll_ids(device: torch.device) -> None:
+    """check_ids, but only if a kernel has used this device's counter yet (cheap no-op before the first forward)"""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key in _err_flags:
+        check_ids(device)
+
+
 # --------------------------------------------------------------------------------------------------
 # kernels, no autograd
 # --------------------------------------------------------------------------------------------------
@@ -606,6 +613,15 @@ class _StepContext:
             pass
 
 
+def bprmf_step_reset() -> None:
+    """Drop every step context's prefetched plan (b2r_bprmf_ctx_reset).  Runners call this at the start of an epoch
+    and when one is aborted: a prefetched plan is recognised by the id tensors' addresses, which the caching
+    allocator may reuse for another batch."""
+    L = _lib.load()
+    for ctx in _step_ctx.values():
+        L.b2r_bprmf_ctx_reset(ctx.handle)
+
+
 def bprmf_train_step(U: torch.nn.Parameter, I: torch.nn.Parameter, optimizer, uid: torch.Tensor,
                      iid: torch.Tensor, next_uid: Optional[torch.Tensor] = None,
                      next_iid: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -630,7 +646,10 @@ def bprmf_train_step(U: torch.nn.Parameter, I: torch.nn.Parameter, optimizer, ui
     if next_uid is not None and next_iid is not None:
         if tuple(next_iid.shape) != (B, Cn) or next_uid.numel() != B:
             raise ValueError("prefetched batch must have the same shape as the current one")
-        next_uid, next_iid = _i64c(next_uid, "next user_id"), _i64c(next_iid, "next item_id")
+        if not (next_uid.is_contiguous() and next_iid.is_contiguous()) or next_uid.dtype != torch.int64 \
+                or next_iid.dtype != torch.int64:
+            # the side stream reads these after this call returns: a temporary contiguous copy would be freed under it
+            raise ValueError("prefetched id tensors must be contiguous int64 tensors that stay alive until the next step")
     else:
         next_uid = next_iid = None
     optimizer.advance()

@@ -119,7 +119,10 @@ class RowSparseOptimizer:
                 if "last" in e:
                     # exact dense-Adam mode: the rows about to be updated must stand at step t-1 (they do already if
                     # before_forward ran) and are stamped t, the step the update below applies
-                    self._advance(e, torch.unique(ids), self.t - 1, stamp=self.t)
+                    upd = torch.unique(ids)
+                    if ign >= 0:
+                        upd = upd[upd != ign]            # padding positions are dropped by the plan: that row is not updated
+                    self._advance(e, upd, self.t - 1, stamp=self.t)
                 plan = ops.make_plan(ids, p.shape[0], p.shape[1], ign, pend[0][0].numel() if ign >= 0 else 0)
                 plan.apply_optimizer(p.data, e["m"], e["v"], self._opt(e["wd"], e["state_ld"]), [x[1] for x in pend])
                 pend.clear()

@@ -74,6 +74,16 @@ class _KernelModelMixin:
     def optimizer(self, value):
         self.__dict__["_b2r_optimizer"] = value
 
+    # Out-of-range ids: the reference's nn.Embedding raises IndexError inside forward (BPRMF.py:39-40); the kernels
+    # clamp the id and count it on the device.  Every runner (the reference's unchanged BaseRunner included) switches
+    # the model between train() and eval() around each fit / predict (BaseRunner.py:179,231), so the counter is polled
+    # there: one synchronising 4-byte read per phase switch, and a bad id surfaces as the same IndexError.
+    def train(self, mode: bool = True):
+        tables = self.sparse_tables()
+        if tables and tables[0].is_cuda:
+            ops.poll_ids(tables[0].device)
+        return super().train(mode)
+
     # models/BaseModel.py:175-189
     def loss(self, out_dict: dict) -> torch.Tensor:
         return ops.bpr_loss(out_dict["prediction"])
@@ -94,6 +104,9 @@ class _KernelModelMixin:
         BaseModel.py:194-198) a dot-product model is ranked without materialising the [B, n_items] scores;
         (mask_row, mask_item) are the (batch row, item id) pairs BaseRunner.py:244-251 would set to -inf."""
         with torch.no_grad():
+            opt = self.__dict__.get("_b2r_optimizer")
+            if getattr(opt, "exact_dense", False) and not self.training:
+                opt.flush()                     # exact dense-Adam mode: ranks must see rows advanced through skipped steps
             item_id = feed_dict["item_id"]
             qr = self.query_rows(feed_dict) if getattr(self, "test_all", 0) else None
             if qr is not None and item_id.shape[1] == self.item_num:

@@ -38,6 +38,14 @@ def format_metric(result: Dict[str, float]) -> str:
     return ",".join(parts)
 
 
+def _poll_ids(model) -> None:
+    """One synchronising poll of the kernels' out-of-range-id counter per epoch / evaluation: the reference's
+    nn.Embedding raises IndexError on a bad id (BPRMF.py:39-40); the kernels clamp and count, so the runner raises."""
+    dev = getattr(model, "device", None)
+    if isinstance(dev, torch.device) and dev.type == "cuda":
+        ops.check_ids(dev if dev.index is not None else None)
+
+
 class BaseRunner:
     @staticmethod
     def parse_runner_args(parser):
@@ -185,15 +193,21 @@ class BaseRunner:
         cur = next(it, None)
         cur = batch_to_device(cur, model.device) if cur is not None else None
         losses = []
-        while cur is not None:
-            nxt = next(it, None)
-            if nxt is not None:
-                nxt = batch_to_device(nxt, model.device)
-            torch.rand(*cur["item_id"].shape)                     # BaseRunner.py:189's draw, see above
-            same_shape = nxt is not None and nxt["item_id"].shape == cur["item_id"].shape
-            losses.append(model.train_step(cur, nxt if same_shape else None))
-            cur = nxt
-        return float(np.mean(torch.stack(losses).cpu().numpy())) if losses else float("nan")
+        ops.bprmf_step_reset()                 # no plan prefetched by an earlier (possibly aborted) epoch survives
+        try:
+            while cur is not None:
+                nxt = next(it, None)
+                if nxt is not None:
+                    nxt = batch_to_device(nxt, model.device)
+                torch.rand(*cur["item_id"].shape)                     # BaseRunner.py:189's draw, see above
+                same_shape = nxt is not None and nxt["item_id"].shape == cur["item_id"].shape
+                losses.append(model.train_step(cur, nxt if same_shape else None))
+                cur = nxt
+        finally:
+            ops.bprmf_step_reset()
+        out = float(np.mean(torch.stack(losses).cpu().numpy())) if losses else float("nan")
+        _poll_ids(model)
+        return out
 
     def fit(self, dataset, epoch=-1) -> float:
         """helpers/BaseRunner.py:174-208, step for step."""
@@ -229,12 +243,17 @@ class BaseRunner:
             loss.backward()
             model.optimizer.step()
             losses.append(loss.detach().cpu().data.numpy())
+        _poll_ids(model)
         return float(np.mean(losses))
 
     def eval_termination(self, criterion: List[float]) -> bool:
-        if len(criterion) > self.early_stop and all(
-                x >= y for x, y in zip(criterion[-self.early_stop:], criterion[-self.early_stop + 1:])):
-            return True
+        """helpers/BaseRunner.py:132-137 with utils.non_increasing (utils/utils.py:103-104): stop when the FIRST value
+        of the last ``early_stop`` results is >= every later one of that window (not a pairwise-monotone test), or when
+        the best result is more than ``early_stop`` epochs old."""
+        if len(criterion) > self.early_stop:
+            w = criterion[-self.early_stop:]
+            if all(w[0] >= y for y in w[1:]):
+                return True
         return len(criterion) - criterion.index(max(criterion)) > self.early_stop
 
     def evaluate(self, dataset, topks: list, metrics: list) -> Dict[str, float]:
@@ -270,6 +289,7 @@ class BaseRunner:
             hist = h if hist is None else hist + h
             n_rows += bs
             start += bs
+        _poll_ids(model)
         return ops.metrics_from_histogram(hist, n_rows, topks, metrics)
 
     def predict(self, dataset, save_prediction: bool = False) -> np.ndarray:
@@ -283,6 +303,7 @@ class BaseRunner:
             batch = batch_to_device(batch, model.device)
             fn = model.inference if hasattr(model, "inference") else model
             preds.extend(fn(batch)["prediction"].cpu().data.numpy())
+        _poll_ids(model)
         preds = np.array(preds)
         if model.test_all:
             rows, cols = [], []

@@ -97,6 +97,12 @@ def test_eval_termination_rule():
     assert not r.eval_termination([0.1, 0.2, 0.3])
     assert r.eval_termination([0.5, 0.4, 0.3, 0.2])            # non-increasing tail
     assert r.eval_termination([0.9, 0.1, 0.2, 0.3, 0.4])       # best is more than early_stop epochs ago
+    # utils.non_increasing (utils/utils.py:103-104) compares the window's FIRST value with every later one -- not
+    # consecutive pairs: [0.5, 0.3, 0.4] stops although 0.3 < 0.4
+    assert r.eval_termination([0.1, 0.5, 0.3, 0.4])
+    assert not r.eval_termination([0.1, 0.3, 0.5, 0.4])
+    r1 = BaseRunner(_args(plugin.BPRMF, ["--early_stop", "1"]))
+    assert r1.eval_termination([0.1, 0.2])                     # a one-element window is trivially non-increasing
 
 
 def test_metrics_from_histogram_equal_evaluate_method():
