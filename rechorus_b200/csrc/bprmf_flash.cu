@@ -1,0 +1,295 @@
+// bprmf_flash.cu -- K1+K2a as ONE streaming pass per sample, no second use of any candidate row.
+//
+// Contract (same as the kernels it replaces, bprmf_fused.cu): gather the user row and the C candidate rows of a
+// sample, score them (models/general/BPRMF.py:39-42), evaluate the BPR loss (models/BaseModel.py:182-185) and its
+// closed-form gradient g, and reduce dQ = sum_c g_c * I[id_c] (the mul/sum half of loss.backward(),
+// helpers/BaseRunner.py:205) -- every candidate row read from HBM exactly once.
+//
+// Why a new structure: the earlier kernels kept all rows of a sample on chip between their two uses (score, then
+// g * row once the softmax over the sample's negatives is known) and were bound by that hand-over (barriers, cross-group
+// statistics, 22 M warp instructions for 105 MB).  The gradient factorises instead.  With e_c = exp(x_c - M),
+// s_c = sigmoid(p - x_c), Z = sum e_c, A = sum e_c s_c, S = A / Z, dS = -1 / (B S):
+//     g_c = dS * (e_c / Z) * ((s_c - S) - s_c (1 - s_c)) = (dS / Z) * e_c * (s_c^2 - S)        (negatives)
+//     dQ  = g_0 * r_0 + (dS / Z) * ( sum_c e_c s_c^2 r_c  -  S * sum_c e_c r_c )
+// so two row-weighted sums (acc1, acc2) and three scalars (Z, A, D = sum e_c s_c (1 - s_c)) can be accumulated while
+// the rows stream through, with the running-max rescaling of an online softmax -- the flash-attention recurrence
+// applied to BPR.  A row is needed for one dot product and two FMAs and is then dead.
+//
+// Decomposition: ONE WARP per sample, no block-level barrier anywhere.  A row is read by LPR = d/4 lanes (16 B each);
+// the warp's 32 / LPR lane groups take alternate negatives.  Rows travel global -> shared memory with cp.async (16 B per
+// lane, nothing held in registers while in flight) through a per-warp ring of ST stages of RCH rows per group, so
+// (ST - 1) * RCH rows per group are always in flight; each lane reads back only the 16 bytes it copied itself.  The
+// sample's ids are fetched first (one coalesced pass) and parked in shared memory as checked 32-bit row indices.  The
+// groups' partial states meet once per sample through shuffles (online-softmax combine, fixed order -> deterministic).
+// All 8 warps x 4 CTAs per SM of a B = 4096 batch are resident at once: a single wave, no tail.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace b2r {
+
+constexpr int kFlWarps = 8;
+
+// sum each of the RCH per-lane values over the LPR lanes of a group with ~RCH + log2(LPR / RCH) shuffles: at every step
+// the lanes split the live values in two halves and exchange the half they give up.  Afterwards lane `sub` holds the
+// total of value sub / (LPR / RCH)  (the LPR / RCH lanes of one block hold copies).
+template <int LPR, int RCH>
+__device__ __forceinline__ float fl_group_sum_multi(float (&v)[RCH], int sub) {
+    int n = RCH;
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        if (n > 1) {
+            const bool upper = (sub & o) != 0;
+            n >>= 1;
+#pragma unroll
+            for (int i = 0; i < (RCH + 1) / 2; ++i) {
+                if (i < n) {
+                    const float send = upper ? v[i] : v[i + n];
+                    const float keep = upper ? v[i + n] : v[i];
+                    v[i] = keep + __shfl_xor_sync(B2R_FULL_MASK, send, o);
+                }
+            }
+        } else {
+            v[0] += __shfl_xor_sync(B2R_FULL_MASK, v[0], o);
+        }
+    }
+    return v[0];
+}
+
+template <int LPR>
+__device__ __forceinline__ float fl_group_max(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(B2R_FULL_MASK, v, o));
+    return v;
+}
+
+__device__ __forceinline__ void fl_cp16(void* smem_dst, const void* gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+template <int LPR, int RCH, int ST>
+__global__ void __launch_bounds__(kFlWarps * 32, (LPR == 32) ? 3 : 4)
+k_bprmf_flash(const float* __restrict__ U, const int64_t* __restrict__ uid, int64_t n_users,
+              const float* __restrict__ T, const int64_t* __restrict__ ids, int64_t n_t,
+              float* __restrict__ pred, float* __restrict__ gout, float* __restrict__ row_loss,
+              float* __restrict__ dQ, float* __restrict__ qout, int B, int C, int cpad, int32_t* err_flag,
+              float* __restrict__ loss_out, unsigned int* __restrict__ done_counter) {
+    constexpr int D = LPR * 4;
+    constexpr int GPW = 32 / LPR;                 // lane groups (rows in parallel) per warp
+    constexpr int RS = LPR / RCH;                 // lanes holding a copy of one row's score after the multi-sum
+    static_assert(RCH <= LPR && (RCH & (RCH - 1)) == 0, "RCH must be a power of two <= LPR");
+    constexpr int STAGE_F4 = RCH * 32;            // float4 per stage per warp: RCH rows per group x 32 lanes
+    extern __shared__ __align__(16) unsigned char fl_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPR, grp = lane / LPR;
+    // per-warp regions: ring [ST][RCH][32] float4, then cpad floats of scores, then cpad row indices
+    unsigned char* wbase = fl_smem + (size_t)warp * ((size_t)ST * STAGE_F4 * 16 + (size_t)cpad * 8);
+    float4* ring = reinterpret_cast<float4*>(wbase);
+    float* xs = reinterpret_cast<float*>(wbase + (size_t)ST * STAGE_F4 * 16);
+    uint32_t* sid = reinterpret_cast<uint32_t*>(xs + cpad);
+    const float invB = 1.f / (float)B;
+
+    for (int64_t b = (int64_t)blockIdx.x * kFlWarps + warp; b < B; b += (int64_t)gridDim.x * kFlWarps) {
+        // ---- ids of the sample: one coalesced pass, range-checked once, parked as 32-bit row indices -------------
+        const int64_t* idp = ids + b * C;
+        for (int c = lane; c < C; c += 32) sid[c] = (uint32_t)checked_id(idp[c], n_t, err_flag);
+        const int64_t qrow = checked_id(uid[b], n_users, lane == 0 ? err_flag : nullptr);
+        __syncwarp();
+        const float4 q = ld4(U + qrow * D + sub * 4);
+        const float4 r0 = ld4(T + (size_t)sid[0] * D + sub * 4);          // the positive's row (every group: same bytes)
+        // negatives of this group: c = 1 + grp + GPW * k, k = 0 .. ; chunk j covers k in [j * RCH, (j + 1) * RCH)
+        const int nneg = C - 1;
+        const int nch = (nneg + GPW * RCH - 1) / (GPW * RCH);               // chunks per group (warp-uniform)
+
+        auto issue = [&](int j) {                                          // request chunk j into stage j % ST
+            if (j < nch) {
+                float4* st = ring + (j % ST) * STAGE_F4 + lane;
+#pragma unroll
+                for (int r = 0; r < RCH; ++r) {
+                    const int c = 1 + grp + GPW * (j * RCH + r);
+                    if (c < C) fl_cp16(st + r * 32, T + (size_t)sid[c] * D + sub * 4);
+                    else st[r * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");        // one (possibly empty) group per call
+        };
+#pragma unroll
+        for (int j = 0; j < ST - 1; ++j) issue(j);
+
+        if (qout != nullptr && grp == 0) st4(qout + b * D + sub * 4, q);
+        const float p = group_sum<LPR>(dot4(q, r0));                      // positive's score, known to every group
+        if (lane == 0) xs[0] = p;
+
+        float M = -INFINITY, Zl = 0.f, Al = 0.f, Dl = 0.f;                 // running max; per-lane partial sums
+        float4 acc1 = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc1;       // sum e s^2 r, sum e r (this lane's 16 B)
+        for (int j = 0; j < nch; ++j) {
+            issue(j + ST - 1);
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(ST - 1) : "memory");
+            const float4* st = ring + (j % ST) * STAGE_F4 + lane;
+            float4 r[RCH];
+            float d[RCH];
+#pragma unroll
+            for (int k = 0; k < RCH; ++k) {
+                r[k] = st[k * 32];
+                d[k] = dot4(q, r[k]);
+            }
+            const float x = fl_group_sum_multi<LPR, RCH>(d, sub);          // score of row sub / RS of this chunk
+            const int c_mine = 1 + grp + GPW * (j * RCH + sub / RS);
+            const bool valid = c_mine < C;
+            if (valid && (sub % RS) == 0) xs[c_mine] = x;
+            const float mx = fl_group_max<LPR>(valid ? x : -INFINITY);
+            const float Mn = fmaxf(M, mx);
+            const float sc = (Mn == -INFINITY) ? 1.f : __expf(M - Mn);     // M = -inf -> 0: nothing accumulated yet
+            M = Mn;
+            const float e = valid ? __expf(x - Mn) : 0.f;
+            const float s = __fdividef(1.f, 1.f + __expf(x - p));
+            const float es = e * s;
+            const bool speak = (sub % RS) == 0;
+            Zl = fmaf(Zl, sc, speak ? e : 0.f);
+            Al = fmaf(Al, sc, speak ? es : 0.f);
+            Dl = fmaf(Dl, sc, speak ? es * (1.f - s) : 0.f);
+            acc1.x *= sc; acc1.y *= sc; acc1.z *= sc; acc1.w *= sc;
+            acc2.x *= sc; acc2.y *= sc; acc2.z *= sc; acc2.w *= sc;
+            const float ess = es * s;
+#pragma unroll
+            for (int k = 0; k < RCH; ++k) {
+                const float ek = __shfl_sync(B2R_FULL_MASK, e, k * RS, LPR);
+                const float wk = __shfl_sync(B2R_FULL_MASK, ess, k * RS, LPR);
+                fma4(acc2, ek, r[k]);
+                fma4(acc1, wk, r[k]);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+
+        // ---- combine: lanes of a group, then the warp's groups (online-softmax rescale), fixed order ---------------
+        float Z = group_sum<LPR>(Zl), A = group_sum<LPR>(Al), Dp = group_sum<LPR>(Dl);
+        if (GPW > 1) {
+            float Mall = M;
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) Mall = fmaxf(Mall, __shfl_xor_sync(B2R_FULL_MASK, Mall, o));
+            const float sg = (M == -INFINITY) ? 0.f : __expf(M - Mall);
+            Z *= sg; A *= sg; Dp *= sg;
+            acc1.x *= sg; acc1.y *= sg; acc1.z *= sg; acc1.w *= sg;
+            acc2.x *= sg; acc2.y *= sg; acc2.z *= sg; acc2.w *= sg;
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                Z += __shfl_xor_sync(B2R_FULL_MASK, Z, o);
+                A += __shfl_xor_sync(B2R_FULL_MASK, A, o);
+                Dp += __shfl_xor_sync(B2R_FULL_MASK, Dp, o);
+                acc1.x += __shfl_xor_sync(B2R_FULL_MASK, acc1.x, o);
+                acc1.y += __shfl_xor_sync(B2R_FULL_MASK, acc1.y, o);
+                acc1.z += __shfl_xor_sync(B2R_FULL_MASK, acc1.z, o);
+                acc1.w += __shfl_xor_sync(B2R_FULL_MASK, acc1.w, o);
+                acc2.x += __shfl_xor_sync(B2R_FULL_MASK, acc2.x, o);
+                acc2.y += __shfl_xor_sync(B2R_FULL_MASK, acc2.y, o);
+                acc2.z += __shfl_xor_sync(B2R_FULL_MASK, acc2.z, o);
+                acc2.w += __shfl_xor_sync(B2R_FULL_MASK, acc2.w, o);
+            }
+            M = Mall;
+        }
+        const float S = (C > 1) ? __fdividef(A, Z) : 0.f;
+        const bool inside = (S >= 1e-8f) && (S <= 1.f - 1e-8f);
+        const float dS = inside ? -__fdividef(invB, S) : 0.f;
+        const float invZ = (C > 1) ? __fdividef(1.f, Z) : 0.f;
+        const float g0 = dS * Dp * invZ;
+        const float kz = dS * invZ;
+        if (grp == 0) {
+            float4 o;
+            o.x = fmaf(g0, r0.x, kz * fmaf(-S, acc2.x, acc1.x));
+            o.y = fmaf(g0, r0.y, kz * fmaf(-S, acc2.y, acc1.y));
+            o.z = fmaf(g0, r0.z, kz * fmaf(-S, acc2.z, acc1.z));
+            o.w = fmaf(g0, r0.w, kz * fmaf(-S, acc2.w, acc1.w));
+            st4(dQ + b * D + sub * 4, o);
+        }
+        if (lane == 0) row_loss[b] = -logf(fminf(fmaxf(S, 1e-8f), 1.f - 1e-8f));
+        __syncwarp();                                                      // xs[] complete
+        // ---- per-candidate gradient (and scores), coalesced ----------------------------------------------------------
+        for (int c = lane; c < C; c += 32) {
+            const float x = xs[c];
+            float g;
+            if (c == 0) {
+                g = g0;
+            } else {
+                const float e = __expf(x - M);
+                const float s = __fdividef(1.f, 1.f + __expf(x - p));
+                g = kz * e * ((s - S) - s * (1.f - s));
+            }
+            gout[b * C + c] = g;
+            if (pred != nullptr) pred[b * C + c] = x;
+        }
+        __syncwarp();                                                      // before the next sample reuses xs / sid / ring
+    }
+
+    // mean of the per-sample losses by the last CTA to finish (fixed summation order -> deterministic)
+    if (loss_out != nullptr) {
+        __shared__ bool last;
+        __shared__ float red[kFlWarps * 32];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            float a = 0.f;
+            for (int i = threadIdx.x; i < B; i += kFlWarps * 32) a += __ldcg(row_loss + i);
+            red[threadIdx.x] = a;
+            __syncthreads();
+            for (int o = kFlWarps * 16; o > 0; o >>= 1) {
+                if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                loss_out[0] = red[0] / (float)B;
+                *done_counter = 0u;
+            }
+        }
+    }
+}
+
+}  // namespace b2r
+
+using namespace b2r;
+
+// returns B2R_E_UNSUPPORTED when the shape is outside the kernel's class (d in {32, 64, 128}, C <= 1024)
+int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
+                           int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, float* qout,
+                           int B, int C, int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter,
+                           b2r_stream_t stream) {
+    if (!(d == 32 || d == 64 || d == 128) || C > 1024 || n_items >= 0xffffffffLL)
+        return set_error(B2R_E_UNSUPPORTED, "bprmf_flash: d=%d C=%d", d, C);
+    const int cpad = (C + 3) / 4 * 4;
+    const int64_t need = ((int64_t)B + kFlWarps - 1) / kFlWarps;
+    const int64_t cap = (int64_t)sm_count() * 32;                         // beyond that, warps loop over samples
+    const int grid = (int)(need < cap ? need : cap);
+    // variant knob for A/B runs: B2R_FLASH="<RCH><ST>" e.g. 43 (default), 44, 26, 28
+    static const int variant = [] { const char* e = getenv("B2R_FLASH"); return e ? atoi(e) : 43; }();
+#define B2R_FL(LPR, RCH, ST)                                                                                         \
+    do {                                                                                                             \
+        const int smem = kFlWarps * (ST * RCH * 32 * 16 + cpad * 8);                                                 \
+        static int attr_smem = 0;                                                                                    \
+        if (smem > attr_smem) {                                                                                      \
+            B2R_CUDA_OK(cudaFuncSetAttribute(k_bprmf_flash<LPR, RCH, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             smem));                                                                 \
+            attr_smem = smem;                                                                                        \
+        }                                                                                                            \
+        k_bprmf_flash<LPR, RCH, ST><<<grid, kFlWarps * 32, smem, as_stream(stream)>>>(                               \
+            U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, qout, B, C, cpad, err_flag, loss_out,   \
+            done_counter);                                                                                           \
+    } while (0)
+#define B2R_FL_D(LPR)                                                                                                \
+    do {                                                                                                             \
+        if (variant == 44) B2R_FL(LPR, 4, 4);                                                                        \
+        else if (variant == 26) B2R_FL(LPR, 2, 6);                                                                   \
+        else if (variant == 28) B2R_FL(LPR, 2, 8);                                                                   \
+        else if (variant == 42) B2R_FL(LPR, 4, 2);                                                                   \
+        else B2R_FL(LPR, 4, 3);                                                                                      \
+    } while (0)
+    if (d == 32) B2R_FL_D(8);
+    else if (d == 64) B2R_FL_D(16);
+    else B2R_FL_D(32);
+#undef B2R_FL_D
+#undef B2R_FL
+    B2R_LAUNCH_OK("k_bprmf_flash");
+    return 0;
+}

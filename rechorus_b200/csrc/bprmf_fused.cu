@@ -303,6 +303,11 @@ int b2r_bprmf_fused_ws_launch(const float* U, const int64_t* uid, int64_t n_user
                               int B, int C, int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter,
                               b2r_stream_t stream);
 
+int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
+                           int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, float* qout,
+                           int B, int C, int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter,
+                           b2r_stream_t stream);
+
 // returns B2R_E_UNSUPPORTED (without touching the error string semantics) when the shape has no fused variant
 static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
                         int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, float* qout, int B,
@@ -333,9 +338,20 @@ static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, con
     B2R_REQUIRE(U && uid && I && iid && grad_pred && row_loss && dQ, B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: null pointer");
     B2R_REQUIRE(B > 0 && C > 0, B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: B=%d C=%d", B, C);
     B2R_REQUIRE(aligned16(U) && aligned16(I) && aligned16(dQ), B2R_E_BADARG, "b2r_bprmf_fused_fwd_bwd: alignment");
-    // B2R_NEXT bit 1: warp-per-sample candidate for the next round (bprmf_fused_ws.cu; unmeasured, off by default)
-    static const int next_bits = [] { const char* e = getenv("B2R_NEXT"); return e ? atoi(e) : 0; }();
-    if ((next_bits & 2) && d == 64 && C <= 104)
+    // Default: the streaming (flash) kernel of bprmf_flash.cu.  B2R_FUSED=v6 selects the CTA-per-sample kernel below,
+    // B2R_FUSED=ws the whole-sample-in-shared-memory warp kernel (bprmf_fused_ws.cu) -- kept for A/B measurements.
+    static const int which = [] {
+        const char* e = getenv("B2R_FUSED");
+        if (e && e[0] == 'v') return 1;
+        if (e && e[0] == 'w') return 2;
+        return 0;
+    }();
+    if (which == 0) {
+        const int rc = b2r_bprmf_flash_launch(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, qout, B, C,
+                                              d, err_flag, loss_out, done_counter, stream);
+        if (rc != B2R_E_UNSUPPORTED) return rc;
+    }
+    if (which == 2 && d == 64 && C <= 104)
         return b2r_bprmf_fused_ws_launch(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, qout, B, C, d,
                                          err_flag, loss_out, done_counter, stream);
     cudaStream_t s = as_stream(stream);

@@ -1,4 +1,5 @@
-// bprmf_fused_ws.cu -- CANDIDATE for the next round (selected with B2R_NEXT=2, never run on a GPU yet, off by default).
+// bprmf_fused_ws.cu -- warp-per-sample variant with the whole sample staged in shared memory (B2R_FUSED=ws; A/B only:
+// 39.0 us alone at config 2 vs 43.6 us for the CTA-per-sample kernel, superseded by bprmf_flash.cu).
 //
 // Same contract as k_bprmf_fused (bprmf_fused.cu): gather the user row and the C candidate rows of a sample, score
 // them, evaluate the BPR loss (models/BaseModel.py:182-185) and its closed-form gradient, reduce
@@ -19,7 +20,6 @@
 //     without redundancy.
 //   * dQ partials of the 8 groups meet in the (by then dead) stage region and are added in group order (deterministic).
 //
-// Expected (not measured): ~900 warp instructions per sample instead of ~5000.
 #include "common.cuh"
 
 namespace b2r {

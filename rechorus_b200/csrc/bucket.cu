@@ -244,7 +244,7 @@ __device__ __forceinline__ void emit_row_heads(const uint64_t* a, int cnt, int b
 }
 
 // ---------------------------------------------------------------------------------------------------
-// CANDIDATE for the next round (selected with B2R_NEXT=1, never measured, off by default): counting sort of a bucket.
+// Counting sort of a bucket (the default; B2R_BUCKET_SORT=bitonic selects the network below instead).
 // The bitonic network costs 36-45 barrier-separated stages per bucket; a bucket's keys span only R = 2^shift rows, so
 // one shared-memory histogram over the rows gives every pair its row's start, an arrival-order slot inside the row,
 // and -- for free -- the row heads.  Rows with several contributions (a minority) are put in ascending position by
@@ -636,13 +636,14 @@ extern "C" int b2r_bucket_partition(const int64_t* ids, int64_t n, int64_t n_row
     k_bucket_scatter<<<grid, kBT, 0, s>>>(ids, n, n_rows, g.shift, ignore_id, ignore_n, cursor, pairs);
     B2R_LAUNCH_OK("k_bucket_scatter");
     const int sort_cap = sm_count() * sort_mul;
-    // B2R_NEXT bit 0: counting-sort candidate for the next round (unmeasured; the default is the bitonic path)
-    static const int next_bits = [] { const char* e = getenv("B2R_NEXT"); return e ? atoi(e) : 0; }();
+    // counting sort per bucket is the default (13.3 us vs 20.8 us per launch at config 2, profiles/README r2);
+    // B2R_BUCKET_SORT=bitonic selects the shared-memory bitonic network for A/B runs (same output)
+    static const bool use_count = [] { const char* e = getenv("B2R_BUCKET_SORT"); return !(e && e[0] == 'b'); }();
     const int sort_grid = g.nb < sort_cap ? g.nb : sort_cap;
     uint64_t* tmp = reinterpret_cast<uint64_t*>(base + L.tmp);
     uint2* longs = reinterpret_cast<uint2*>(base + L.longs);
     uint4* heads = reinterpret_cast<uint4*>(base + L.heads);
-    if (next_bits & 1)
+    if (use_count)
         k_bucket_sort<true><<<sort_grid, kBT, 0, s>>>(pairs, tmp, off, g.nb, off + g.nb + 2, longs, L.long_cap,
                                                       off + g.nb + 3, heads, g.shift);
     else

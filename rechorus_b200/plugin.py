@@ -32,8 +32,9 @@ from . import ops
 # ======================================================================================================
 
 
-# opt-in groundwork for the next round (not yet run on a GPU): SASRec's last block for one query per sequence
-_SASREC_LASTQ = os.environ.get("B2R_SASREC_LASTQ") == "1"
+# SASRec's last block is computed for the one query per sequence whose output is used (exact; 7.56 -> 5.32 ms per
+# config-4 step, profiles/README r2).  B2R_SASREC_LASTQ=0 runs the full block instead (A/B).
+_SASREC_LASTQ = os.environ.get("B2R_SASREC_LASTQ", "1") != "0"
 
 
 class _KernelModelMixin:
@@ -300,7 +301,7 @@ class SASRecKernels(_KernelModelMixin):
     def _last_block_one_query(self, blk, x, history, lengths):
         """The last block for the only position whose output SASRec uses (len-1, SASRec.py:74-81): keys and values from
         every position, query / residual LayerNorms / FFN for that one row per sequence.  Same result as the full block
-        followed by select_last; opt-in groundwork (B2R_SASREC_LASTQ=1), dropout-free path only."""
+        followed by select_last (dropout-free path only; with dropout the full block runs)."""
         a = blk.masked_attn_head
         ones = torch.ones_like(history)
         x_last = ops.select_last(x, ones, lengths)                               # raw row len-1 (no padding mask yet)

@@ -53,10 +53,38 @@ def main():
         for k, v in model.state_dict().items():
             blob["w1:" + k] = v.detach().numpy().copy()
         blob["losses"] = np.array(losses, dtype=np.float64)
+        # The same two epochs in float64 (same initial weights, batches and permutations): how far the reference's OWN
+        # fp32 result sits from the exact one.  Adam divides every gradient entry by its running magnitude, so entries
+        # whose gradient is rounding-level noise take lr-sized steps in any fp32 implementation; "w1_64:" lets a test
+        # bound another implementation's deviation by the reference's own rounding sensitivity instead of a guess.
+        corpus64 = fit_corpus.build()
+        torch.manual_seed(5)
+        model64 = cls(a, corpus64)
+        model64.apply(model64.init_weights)
+        model64.double()
+        data64 = cls.Dataset(model64, corpus64, "train")
+        rand32 = torch.rand
+        torch.rand = lambda *sz, **kw: rand32(*sz, dtype=torch.float32, **kw).double()   # same CPU RNG consumption
+        torch.set_default_dtype(torch.float64)
+        try:
+            runner64 = BaseRunner(a)
+            np.random.seed(42)
+            torch.manual_seed(42)
+            losses64 = [runner64.fit(data64, epoch=e + 1) for e in range(fit_corpus.EPOCHS)]
+        finally:
+            torch.set_default_dtype(torch.float32)
+            torch.rand = rand32
+        for k, v in model64.state_dict().items():
+            blob["w1_64:" + k] = v.detach().numpy().astype(np.float64)
+        blob["losses64"] = np.array(losses64, dtype=np.float64)
         for k, v in metrics.items():
             blob["m:" + k] = np.float64(v)
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **blob)
+        dd = np.concatenate([np.abs(blob["w1:" + k].astype(np.float64) - blob["w1_64:" + k]).ravel()
+                             for k in model.state_dict()])
+        print(name, "fp32-vs-fp64 reference: median %.3g q90 %.3g max %.3g" % (np.median(dd), np.quantile(dd, 0.9), dd.max()),
+              "losses64", [round(x, 6) for x in losses64])
         print(name, "losses", [round(x, 6) for x in losses], {k: round(float(v), 4) for k, v in metrics.items()},
               os.path.getsize(path), "B")
 

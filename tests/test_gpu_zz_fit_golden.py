@@ -42,20 +42,23 @@ def test_bprmf_two_epochs_equal_reference_runner():
             assert abs(metrics[k[2:]] - float(gold[k])) <= 1.0 / 48 + 1e-9, (k, metrics[k[2:]], float(gold[k]))
 
 
-@pytest.mark.skipif(os.environ.get("B2R_NEXT") is None,
-                    reason="written after this round's GPU budget was spent: first run is tools/gpu_next_round.sh")
 @pytest.mark.parametrize("case", ["fit_neumf", "fit_sasrec"])
 def test_deep_models_two_epochs_track_reference_runner(case):
     name = fit_corpus.CASES[case][0]
     gold, losses, metrics, final = run_case(case, _cls(name), torch.device("cuda", 0), ["--table_mode", "dense"])
     assert np.allclose(losses, gold["losses"], rtol=0, atol=1e-4), (losses, gold["losses"])
-    ref = _gold_final(gold)
-    diffs = torch.cat([(final[k] - v).abs().reshape(-1) for k, v in ref.items() if "k_linear.bias" not in k])
-    # the bulk of the parameters (embedding rows with real gradients, untouched rows) agrees to rounding; the tail is
-    # Adam's noise amplification on near-zero gradients, bounded by the total step budget lr * steps
-    assert float(diffs.median()) <= 1e-6
-    assert float(diffs.quantile(0.9)) <= 1e-4
-    assert float(diffs.max()) <= 0.01 * 12
+    keys = [k[3:] for k in gold.files if k.startswith("w1:")]
+    dev = torch.cat([(final[k].double() - torch.from_numpy(gold["w1:" + k]).double()).abs().reshape(-1) for k in keys])
+    # The yardstick is the reference's OWN rounding sensitivity on this run: the same two epochs of the unmodified
+    # reference in float64 ("w1_64:", tests/golden/make_fit_golden.py).  Where the fp32 reference itself sits 2e-5
+    # (median) to 0.1 (max) away from the exact result -- NeuMF near its flat start: gradient entries are rounding
+    # noise and Adam turns them into lr-sized steps -- no fp32 implementation can be asked to sit closer to it.
+    ref = torch.cat([(torch.from_numpy(gold["w1:" + k]).double() - torch.from_numpy(gold["w1_64:" + k])).abs().reshape(-1)
+                     for k in keys])
+    for name_q, q in (("median", 0.5), ("q90", 0.9), ("q99", 0.99)):
+        got, yard = float(dev.quantile(q)), float(ref.quantile(q))
+        assert got <= max(1e-6, 4.0 * yard), (case, name_q, got, yard)
+    assert float(dev.max()) <= max(1e-4, 4.0 * float(ref.max())), (case, float(dev.max()), float(ref.max()))
     for k in gold.files:
         if k.startswith("m:"):
             assert 0.0 <= metrics[k[2:]] <= 1.0 and abs(metrics[k[2:]] - float(gold[k])) <= 0.15, k
