@@ -294,8 +294,8 @@ B2R_API int b2r_colscale(const float* a, const float* w, float* out, int64_t row
 B2R_API int b2r_colsum_prod(const float* a, const float* b, float* out, int64_t rows, int d, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Groundwork for row f3 (not used by the default paths of this round): the per-epoch negative sampling of
- * models/BaseModel.py:206-214 on the device.  out[i*K + j] is uniform over the items of [1, n_items) that are not in
+ * Row f3, batch production on the device (opt-in): the per-epoch negative sampling of
+ * models/BaseModel.py:206-214.  out[i*K + j] is uniform over the items of [1, n_items) that are not in
  * the training clicks of user_ids[i] (CSR: clicked_ptr [n_users+1], clicked_items sorted ascending and unique per user,
  * all within [1, n_items)).  No rejection loop: with m clicks the user has A = n_items-1-m allowed items; r =
  * floor(x * A / 2^32), x = word 0 of Philox4x32-10(counter = (lo32(i*K+j), hi32(i*K+j), 0, epoch), key = seed), and
@@ -305,6 +305,11 @@ B2R_API int b2r_colsum_prod(const float* a, const float* b, float* out, int64_t 
 B2R_API int b2r_sample_negatives(const int64_t* user_ids, int64_t N, int K, const int64_t* clicked_ptr,
                                  const int64_t* clicked_items, int64_t n_users, int64_t n_items, uint64_t seed,
                                  uint32_t epoch, int64_t* out, int32_t* err_flag, b2r_stream_t stream);
+/* One training batch of a GeneralModel assembled on the device (GeneralModel.Dataset._get_feed_dict + collate_batch,
+ * models/BaseModel.py:192-203,135-152): batch row t is training row perm[start + t] (perm NULL: start + t);
+ * out_uid[t] = users[row], out_iid[t, 0] = items[row], out_iid[t, 1 + k] = neg[row, k]. */
+B2R_API int b2r_collate_general(const int64_t* users, const int64_t* items, const int64_t* neg, const int64_t* perm,
+                                int64_t start, int Bn, int K, int64_t* out_uid, int64_t* out_iid, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Groundwork for the exact dense-Adam mode (not used by the default paths of this round): advance rows of a table whose

@@ -1,5 +1,5 @@
-// sampler.cu -- groundwork for SURVEY.md §8 row f3 (not used by any default path of this round, not yet run on a GPU):
-// the per-epoch negative sampling of models/BaseModel.py:206-214 on the device.
+// sampler.cu -- SURVEY.md §8 row f3, batch production on the device (opt-in: --device_sampler / --device_batches):
+// the per-epoch negative sampling of models/BaseModel.py:206-214 and the collate of models/BaseModel.py:192-203,135-152.
 //
 // Reference semantics: for every training row i (user u_i) and every j < K draw an item uniformly from [1, n_items)
 // and redraw while it is in the user's training clicks -- the result is uniform over the user's non-clicked items,
@@ -64,9 +64,44 @@ k_sample_negatives(const int64_t* __restrict__ user_ids, int64_t N, int K, const
     }
 }
 
+// One training batch of a GeneralModel assembled on the device: what GeneralModel.Dataset._get_feed_dict
+// (models/BaseModel.py:192-203) + collate_batch (:135-152) build on the host sample by sample.  Row t of the batch is
+// training row perm[start + t] (perm NULL: identity): user_id[t] = users[row], item_id[t] = [items[row], neg[row, 0..K)].
+__global__ void __launch_bounds__(256)
+k_collate_general(const int64_t* __restrict__ users, const int64_t* __restrict__ items, const int64_t* __restrict__ neg,
+                  const int64_t* __restrict__ perm, int64_t start, int Bn, int K, int64_t* __restrict__ out_uid,
+                  int64_t* __restrict__ out_iid) {
+    const int C = K + 1;
+    const int64_t total = (int64_t)Bn * C;
+    for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+        const int t = (int)(idx / C), c = (int)(idx - (int64_t)t * C);
+        const int64_t row = perm ? perm[start + t] : start + t;
+        if (c == 0) {
+            out_uid[t] = users[row];
+            out_iid[idx] = items[row];
+        } else {
+            out_iid[idx] = neg[row * K + (c - 1)];
+        }
+    }
+}
+
 }  // namespace b2r
 
 using namespace b2r;
+
+extern "C" int b2r_collate_general(const int64_t* users, const int64_t* items, const int64_t* neg, const int64_t* perm,
+                                   int64_t start, int Bn, int K, int64_t* out_uid, int64_t* out_iid, b2r_stream_t stream) {
+    B2R_REQUIRE(users && items && neg && out_uid && out_iid, B2R_E_BADARG, "b2r_collate_general: null pointer");
+    B2R_REQUIRE(Bn >= 0 && K >= 1 && start >= 0, B2R_E_BADARG, "b2r_collate_general: Bn=%d K=%d", Bn, K);
+    if (Bn == 0) return 0;
+    const int64_t total = (int64_t)Bn * (K + 1);
+    int64_t grid = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    k_collate_general<<<(int)grid, 256, 0, as_stream(stream)>>>(users, items, neg, perm, start, Bn, K, out_uid, out_iid);
+    B2R_LAUNCH_OK("k_collate_general");
+    return 0;
+}
 
 extern "C" int b2r_sample_negatives(const int64_t* user_ids, int64_t N, int K, const int64_t* clicked_ptr,
                                     const int64_t* clicked_items, int64_t n_users, int64_t n_items, uint64_t seed,

@@ -273,6 +273,22 @@ class DeviceNegativeSampler:
         return out
 
 
+def collate_general(users: torch.Tensor, items: torch.Tensor, neg: torch.Tensor, perm: Optional[torch.Tensor], start: int,
+                    Bn: int, out_uid: torch.Tensor, out_iid: torch.Tensor) -> None:
+    """b2r_collate_general: one GeneralModel training batch assembled on the device (BaseModel.py:192-203,135-152)"""
+    _need_cuda(users, items, neg, perm, out_uid, out_iid)
+    K = neg.shape[1]
+    if out_iid.shape[1] != K + 1 or out_iid.shape[0] < Bn or out_uid.numel() < Bn:
+        raise ValueError("collate_general: output buffers do not fit the batch")
+    for t in (users, items, neg, out_uid, out_iid):
+        if t.dtype != torch.int64 or not t.is_contiguous():
+            raise TypeError("collate_general: contiguous int64 tensors expected")
+    if perm is not None and (perm.dtype != torch.int64 or not perm.is_contiguous()):
+        raise TypeError("collate_general: perm must be contiguous int64")
+    _lib.check(_lib.load().b2r_collate_general(_p(users), _p(items), _p(neg), _p(perm), int(start), int(Bn), int(K),
+                                               _p(out_uid), _p(out_iid), _stream()), "b2r_collate_general")
+
+
 def adam_exact_advance(W: torch.Tensor, m: torch.Tensor, v: torch.Tensor, last: torch.Tensor, upto: int, opt,
                        rows: Optional[torch.Tensor] = None, stamp: int = 0, state_ld: int = 0) -> None:
     """Groundwork for the exact dense-Adam mode (b2r_adam_exact_advance): bring the listed unique rows (all rows when

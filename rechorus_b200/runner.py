@@ -71,10 +71,13 @@ class BaseRunner:
                                  "as one C call (forward, loss, backward, optimizer; next batch's plan prefetched)")
         parser.add_argument("--exact_adam", type=int, default=0,
                             help="1 (with --fused_optimizer 1, Adam): row-sparse cost, dense torch.optim.Adam results "
-                                 "(rows are advanced through their skipped steps; next-round groundwork)")
+                                 "(rows are advanced through their skipped steps)")
         parser.add_argument("--device_sampler", type=int, default=0,
                             help="non-zero seed: draw the training negatives on the GPU every epoch (same distribution "
-                                 "as BaseModel.py:206-214, counter-based stream; next-round groundwork)")
+                                 "as BaseModel.py:206-214, counter-based stream)")
+        parser.add_argument("--device_batches", type=int, default=0,
+                            help="non-zero (a value > 1 is the seed): the whole epoch's batch production on the GPU -- "
+                                 "negatives, row shuffle and collate as device kernels (runner.fit_on_device; GeneralModel)")
         parser.add_argument("--device_metrics", type=int, default=0,
                             help="1: rank the ground truth on the GPU (model.eval_ranks) instead of copying predictions "
                                  "to the host for evaluate_method")
@@ -116,6 +119,7 @@ class BaseRunner:
         self.fused_step = getattr(args, "fused_step", 0)
         self.exact_adam = getattr(args, "exact_adam", 0)
         self.device_sampler = getattr(args, "device_sampler", 0)
+        self.device_batches = getattr(args, "device_batches", 0)
         self.topk = [int(x) for x in args.topk.split(",")]
         self.metrics = [m.strip().upper() for m in args.metric.split(",")]
         self.main_metric = args.main_metric or f"{self.metrics[0]}@{self.topk[0]}"
@@ -209,6 +213,77 @@ class BaseRunner:
         _poll_ids(model)
         return out
 
+    def fit_on_device(self, dataset, epoch=-1) -> float:
+        """the same epoch with BATCH PRODUCTION on the GPU (``--device_batches <seed>``).  What the
+        reference does on the host -- draw the negatives (models/BaseModel.py:206-214), shuffle the rows (the
+        DataLoader's RandomSampler), build one feed dict per sample and collate them (BaseModel.py:192-203,135-152) --
+        becomes three device operations: ``b2r_sample_negatives`` (one Philox draw + one binary search per negative, the
+        reference's distribution from a counter-based stream), a device permutation, and ``b2r_collate_general`` per
+        batch.  The training step is the model's ``train_step`` (one C call) or, for models without one, the plugin
+        contract's forward / loss / backward / optimizer.step on the device batch.  GeneralModel datasets only (a
+        SequentialModel needs the history CSR on the device too).  RNG: the host streams of the reference are NOT
+        reproduced (a sequential NumPy / torch CPU stream cannot be drawn in parallel); results are reproducible from
+        (seed, epoch)."""
+        model = dataset.model
+        if "history_items" in dataset._get_feed_dict(0):
+            raise ValueError("fit_on_device: sequential datasets are not supported (history collate is host-side)")
+        if model.optimizer is None:
+            model.optimizer = self._build_optimizer(model)
+        dev = model.device
+        st = dataset.__dict__.get("_b2r_dev")
+        if st is None:
+            corpus = dataset.corpus
+            seed = int(self.device_batches) if int(self.device_batches) > 1 else 2023
+            st = {"users": torch.as_tensor(np.asarray(dataset.data["user_id"], dtype=np.int64)).to(dev),
+                  "items": torch.as_tensor(np.asarray(dataset.data["item_id"], dtype=np.int64)).to(dev),
+                  "sampler": ops.DeviceNegativeSampler(corpus.train_clicked_set, corpus.n_users, corpus.n_items, dev, seed=seed),
+                  "gen": torch.Generator(device=dev), "seed": seed, "epoch": 0}
+            dataset.__dict__["_b2r_dev"] = st
+        st["epoch"] += 1
+        N, K, B = st["users"].numel(), int(model.num_neg), int(self.batch_size)
+        neg = st["sampler"].sample(st["users"], K, st["epoch"])                     # [N, K] int64 on the device
+        st["gen"].manual_seed(st["seed"] * 1_000_003 + st["epoch"])
+        perm = torch.randperm(N, device=dev, generator=st["gen"])
+        model.train()
+        use_step = hasattr(model, "train_step") and isinstance(model.optimizer, RowSparseOptimizer)
+        n_steps = (N + B - 1) // B
+        NB = 3                                                                       # batch buffers: current, next, one being refilled
+        bufs = st.get("bufs")
+        if bufs is None or bufs[0]["item_id"].shape != (B, K + 1):
+            bufs = st["bufs"] = [{"user_id": torch.empty(B, dtype=torch.int64, device=dev),
+                                  "item_id": torch.empty((B, K + 1), dtype=torch.int64, device=dev),
+                                  "batch_size": B, "phase": "train"} for _ in range(NB)]
+
+        def batch(k):
+            Bn = min(B, N - k * B)
+            buf = bufs[k % NB]
+            ops.collate_general(st["users"], st["items"], neg, perm, k * B, Bn, buf["user_id"], buf["item_id"])
+            if Bn == B:
+                return buf
+            return {"user_id": buf["user_id"][:Bn], "item_id": buf["item_id"][:Bn], "batch_size": Bn, "phase": "train"}
+
+        losses = []
+        ops.bprmf_step_reset()
+        try:
+            cur = batch(0)
+            for k in range(n_steps):
+                nxt = batch(k + 1) if k + 1 < n_steps else None
+                if use_step:
+                    same = nxt is not None and nxt["item_id"].shape == cur["item_id"].shape
+                    losses.append(model.train_step(cur, nxt if same else None))
+                else:
+                    model.optimizer.zero_grad()
+                    loss = model.loss(model(cur))
+                    loss.backward()
+                    model.optimizer.step()
+                    losses.append(loss.detach())
+                cur = nxt
+        finally:
+            ops.bprmf_step_reset()
+        out = float(torch.stack(losses).mean().cpu()) if losses else float("nan")
+        _poll_ids(model)
+        return out
+
     def fit(self, dataset, epoch=-1) -> float:
         """helpers/BaseRunner.py:174-208, step for step."""
         model = dataset.model
@@ -218,6 +293,8 @@ class BaseRunner:
             corpus = dataset.corpus
             model.__dict__["_b2r_device_sampler"] = ops.DeviceNegativeSampler(
                 corpus.train_clicked_set, corpus.n_users, corpus.n_items, model.device, seed=self.device_sampler)
+        if self.device_batches:
+            return self.fit_on_device(dataset, epoch)
         dataset.actions_before_epoch()
         model.train()
         if self.fused_step and hasattr(model, "train_step") and isinstance(model.optimizer, RowSparseOptimizer):

@@ -97,10 +97,16 @@ def _bucket_by_owner(owner: torch.Tensor, world: int):
 class ShardedBPRMF:
     def __init__(self, n_users: int, n_items: int, d: int, device, backend=None, group=None, optimizer: str = "Adam",
                  lr: float = 1e-3, l2: float = 0.0, betas=(0.9, 0.999), eps: Optional[float] = None,
-                 cap_factor: float = 1.25, seed: int = 0, init_std: float = 0.01):
+                 cap_factor: float = 1.25, seed: int = 0, init_std: float = 0.01, world_override: Optional[int] = None):
+        """world_override=1: hold the WHOLE table on this rank and exchange nothing even inside an initialised process
+        group (the 1-GPU anchor of the scaling curve, run by one rank while the others wait)"""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if world_override is not None:
+            if world_override != 1:
+                raise ValueError("world_override can only force the single-rank form")
+            self.world, self.rank = 1, 0
         self.n_users, self.n_items, self.d, self.device = n_users, n_items, d, device
         self.rows_u = math.ceil(n_users / self.world)
         self.rows_i = math.ceil(n_items / self.world)
@@ -166,6 +172,26 @@ class ShardedBPRMF:
         out = torch.empty((x.shape[0] // self.world,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         dist.reduce_scatter_tensor(out, x.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
         return out
+
+    def exchange_description(self) -> str:
+        if self.world == 1:
+            return "none (single rank)"
+        p2p = os.environ.get("B2R_SHARD_P2P") == "1"
+        return ("score routing; scores returned by peer stores from inside the owners' scoring kernel (symmetric memory), "
+                "other hops NCCL all-to-all / all-gather / reduce-scatter" if p2p else
+                "score routing over NCCL: all-to-all x6, all-gather, reduce-scatter per step")
+
+    def nvlink_bytes_per_step(self, B: int, C: int) -> int:
+        """bytes this rank sends to peers per step (the (W-1)/W remote share of every hop)"""
+        W, d = self.world, self.d
+        if W == 1:
+            return 0
+        cap = self.capacity(B * C)
+        per_dest = (B * 8 + B * d * 4                       # user ids out, user vectors back
+                    + cap * 8 + cap * 4 + cap * 4            # pairs out, scores back, g out
+                    + B * d * 4                              # dQ rows to the user-row owners
+                    + B * d * 4)                             # reduce-scatter share of the dQ partials
+        return int((W - 1) * (per_dest + B * d * 4))         # + all-gather of the user vectors
 
     def capacity(self, n: int) -> int:
         if self.world == 1:

@@ -142,3 +142,92 @@ def test_runner_with_device_sampler_trains_on_valid_negatives():
     assert not np.array_equal(neg1, neg2)                   # a fresh draw every epoch
     for i, u in enumerate(train.data["user_id"]):
         assert not (set(neg1[i].tolist()) & corpus.train_clicked_set[u])
+
+
+def test_collate_general_equals_host_collate_bit_for_bit():
+    """integer work: b2r_collate_general vs GeneralModel.Dataset._get_feed_dict + collate_batch (BaseModel.py:192-203,135-152)
+    restated with torch indexing; identity and permuted order, ragged last batch"""
+    from rechorus_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    N, K, B = 1000, 7, 96
+    users = torch.randint(1, 50, (N,), generator=g).cuda()
+    items = torch.randint(1, 80, (N,), generator=g).cuda()
+    neg = torch.randint(1, 80, (N, K), generator=g).cuda()
+    for perm in (None, torch.randperm(N, generator=g).cuda()):
+        for start in (0, 96 * 5, N - 40):
+            Bn = min(B, N - start)
+            ou = torch.full((B,), -1, dtype=torch.int64, device="cuda")
+            oi = torch.full((B, K + 1), -1, dtype=torch.int64, device="cuda")
+            ops.collate_general(users, items, neg, perm, start, Bn, ou, oi)
+            rows = torch.arange(start, start + Bn, device="cuda") if perm is None else perm[start:start + Bn]
+            assert torch.equal(ou[:Bn], users[rows])
+            assert torch.equal(oi[:Bn], torch.cat([items[rows].unsqueeze(1), neg[rows]], dim=1))
+            assert bool((ou[Bn:] == -1).all()) and bool((oi[Bn:] == -1).all())        # nothing beyond the batch is written
+
+
+@pytest.mark.parametrize("model_name", ["BPRMF", "NeuMF"])
+def test_fit_on_device_epoch_equals_the_same_batches_fed_by_hand(model_name):
+    """--device_batches: an epoch whose negatives, row order and collate come from device kernels must train exactly as the
+    same batches handed to the model one by one; its negatives are never training clicks of the row's user"""
+    import argparse
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import fit_corpus
+    from rechorus_b200 import ops, plugin
+    from rechorus_b200.optim import RowSparseOptimizer
+    from rechorus_b200.runner import BaseRunner
+    cls = getattr(plugin, model_name)
+
+    def build():
+        p = argparse.ArgumentParser()
+        p = BaseRunner.parse_runner_args(p)
+        p = cls.parse_model_args(p)
+        a = p.parse_args(["--emb_size", "64", "--num_neg", "5", "--batch_size", "64", "--num_workers", "0", "--lr", "0.05",
+                          "--optimizer", "SGD", "--table_mode", "fused", "--fused_optimizer", "1", "--fused_step", "1",
+                          "--device_batches", "77"])
+        a.device, a.model_path, a.log_file = torch.device("cuda", 0), "/tmp/_b2r_db.pt", ""
+        corpus = fit_corpus.build()
+        torch.manual_seed(1)
+        model = cls(a, corpus).to(a.device)
+        with torch.no_grad():
+            for prm in model.parameters():
+                prm.mul_(20.0)
+        return a, corpus, model, cls.Dataset(model, corpus, "train"), BaseRunner(a)
+
+    a, corpus, model, train, runner = build()
+    l1 = runner.fit(train, epoch=1)                          # routed to fit_on_device by the flag
+    st = train.__dict__["_b2r_dev"]
+    N, K, B = st["users"].numel(), 5, 64
+    neg = st["sampler"].sample(st["users"], K, 1)            # same (seed, epoch) -> same draw
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(st["seed"] * 1_000_003 + 1)
+    perm = torch.randperm(N, device="cuda", generator=gen)
+    users_h = st["users"].cpu().numpy()
+    negs_h = neg.cpu().numpy()
+    for i in range(N):
+        assert not (set(negs_h[i].tolist()) & corpus.train_clicked_set[int(users_h[i])])
+    assert negs_h.min() >= 1 and negs_h.max() < corpus.n_items
+    # the same epoch by hand on a fresh, identically initialised model
+    _, _, model2, _, _ = build()
+    model2.optimizer = RowSparseOptimizer(model2, "SGD", lr=0.05, l2=0.0)
+    model2.set_table_mode("fused")
+    model2.train()
+    losses = []
+    for k in range((N + B - 1) // B):
+        rows = perm[k * B:(k + 1) * B]
+        feed = {"user_id": st["users"][rows].contiguous(), "batch_size": rows.numel(), "phase": "train",
+                "item_id": torch.cat([st["items"][rows].unsqueeze(1), neg[rows]], dim=1).contiguous()}
+        if hasattr(model2, "train_step"):
+            losses.append(model2.train_step(feed))
+        else:
+            model2.optimizer.zero_grad()
+            ls = model2.loss(model2(feed))
+            ls.backward()
+            model2.optimizer.step()
+            losses.append(ls.detach())
+    assert abs(float(torch.stack(losses).mean()) - l1) <= 1e-6
+    for (k, pa), (_, pb) in zip(model.named_parameters(), model2.named_parameters()):
+        assert torch.equal(pa, pb), k
+    l2 = runner.fit(train, epoch=2)
+    assert np.isfinite(l2) and l2 < l1                       # it trains
+    ops.check_ids()
