@@ -720,11 +720,11 @@ def run_c5(args, rank, world, local_rank, sampler, steps_cap, group=None, solo=F
 
 CPU_SAMPLE = {   # bounded samples: (steps, n_items override, note)
     "c1": dict(rows=None, note="one full epoch (568,761 rows, 2,222 steps of 256)"),
-    "c2": dict(steps=6, note="6 full-size steps (B=4096, C=100) over the full 1M x 1M tables"),
-    "c3": dict(steps=4, note="4 full-size steps (B=4096, C=5) over four full 1M x 64 tables"),
-    "c4": dict(steps=2, note="2 full-size steps (B=4096, C=100, L=50)"),
+    "c2": dict(steps=6, note="full-size steps (B=4096, C=100) over the full 1M x 1M tables"),
+    "c3": dict(steps=4, note="full-size steps (B=4096, C=5) over four full 1M x 64 tables"),
+    "c4": dict(steps=2, note="full-size steps (B=4096, C=100, L=50)"),
     "c5": dict(steps=3, n_items=2_000_000, n_users=1_000_000,
-               note="3 steps of B=4096, C=256, d=128 with the item table cut to 2 M rows: the reference's dense gradient + "
+               note="steps of B=4096, C=256, d=128 with the item table cut to 2 M rows: the reference's dense gradient + "
                     "dense Adam over 100 M x 128 would need 205 GB of host memory and minutes per step (its cost grows with "
                     "the table; the cut favours the CPU)"),
 }
@@ -743,11 +743,13 @@ def cpu_leg(wname, steps_override=None):
     src = ref_arm.reference_src()
     if src is not None:
         corpus = ref_arm.synthetic_corpus(w["n_users"], w["n_items"], rows, seed=7, with_history=w.get("L", 0))
-        r = ref_arm.reference_fit(w["model"], model_flags(w), corpus, B)
+        r = ref_arm.reference_fit(w["model"], model_flags(w), corpus, B, warm_epoch=(wname != "c1"))
         value = r["rows"] * C / r["loop_s"]
+        n_st = max(1, (r["rows"] + B - 1) // B)
         return {"value": round(value, 1), "unit": UNIT, "cores": cores, "os_cpu_count": os.cpu_count(), "kind": "reference",
                 "ms_per_step": round(r["loop_s"] * 1e3 / max(1, (r["rows"] + B - 1) // B), 2),
-                "sample": s["note"] + "; the UNMODIFIED reference classes (" + os.path.relpath(src, ROOT) + ") through their own "
+                "sample": (f"{n_st} " if wname != "c1" else "") + s["note"] + (" after one untimed warm-up epoch of the same "
+                          "size" if wname != "c1" else "") + "; the UNMODIFIED reference classes (" + os.path.relpath(src, ROOT) + ") through their own "
                           "BaseRunner.fit on CPU, num_workers=0; the epoch's Python negative sampling ("
                           + f"{r['sample_s']:.1f} s) is timed separately and not counted",
                 "fit_s": round(r["fit_s"], 2), "loss": round(float(r["loss"]), 6)}
@@ -766,7 +768,7 @@ def cpu_leg(wname, steps_override=None):
     r = ref_arm.port_steps(w["model"], params, batches)
     return {"value": round(B * C * r["steps"] / r["loop_s"], 1), "unit": UNIT, "cores": cores, "os_cpu_count": os.cpu_count(),
             "kind": "port", "ms_per_step": round(r["loop_s"] * 1e3 / r["steps"], 2),
-            "sample": s["note"] + "; oracle port of BaseRunner.py:184-207 (the reference tree is not on this box)"}
+            "sample": f"{r['steps']} " + s["note"] + "; oracle port of BaseRunner.py:184-207 (the reference tree is not on this box)"}
 
 
 def run_reference_arm(args, rank):

@@ -80,7 +80,7 @@ def _ref_modules(src):
     return RR.BaseRunner, {"BPRMF": MB.BPRMF, "NeuMF": MN.NeuMF, "SASRec": MS.SASRec}
 
 
-def reference_fit(model_name, model_flags, corpus, batch_size, lr=1e-3, l2=0.0):
+def reference_fit(model_name, model_flags, corpus, batch_size, lr=1e-3, l2=0.0, warm_epoch=True):
     """One ``BaseRunner.fit`` epoch of the unmodified reference on CPU (num_workers 0).  Returns seconds spent in the
     training loop proper (fit minus its own negative-sampling pass, timed separately so the step metric compares with
     a GPU step that is fed pre-drawn negatives), the sampling seconds, rows, and the epoch loss."""
@@ -104,10 +104,18 @@ def reference_fit(model_name, model_flags, corpus, batch_size, lr=1e-3, l2=0.0):
     t0 = time.perf_counter()
     data.actions_before_epoch()                          # the reference's own sampler (BaseModel.py:206-214), timed alone
     t_sample = time.perf_counter() - t0
+    t_warm = None
+    if warm_epoch:
+        # untimed first epoch: first-touch page faults of the dense gradient / Adam state (gigabytes at 1 M rows) and
+        # thread-pool start-up would otherwise be billed to a sample of a handful of steps
+        t0 = time.perf_counter()
+        runner.fit(data, epoch=0)
+        t_warm = time.perf_counter() - t0
     t0 = time.perf_counter()
     loss = runner.fit(data, epoch=1)                     # samples again, then the loop of BaseRunner.py:184-207
     t_fit = time.perf_counter() - t0
-    return {"loop_s": max(t_fit - t_sample, 1e-9), "fit_s": t_fit, "sample_s": t_sample, "rows": len(data), "loss": loss}
+    return {"loop_s": max(t_fit - t_sample, 1e-9), "fit_s": t_fit, "sample_s": t_sample, "rows": len(data), "loss": loss,
+            "warm_epoch_s": t_warm}
 
 
 def port_steps(model_name, params, batches, lr=1e-3, l2=0.0, warmup=1):
