@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "plan_direct.cuh"
 
 namespace b2r {
 
@@ -306,7 +307,7 @@ int b2r_bprmf_fused_ws_launch(const float* U, const int64_t* uid, int64_t n_user
 int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
                            int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, float* qout,
                            int B, int C, int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter,
-                           b2r_stream_t stream);
+                           const b2r::DirectPlanDev* plan_i, const b2r::DirectPlanDev* plan_u, b2r_stream_t stream);
 
 // returns B2R_E_UNSUPPORTED (without touching the error string semantics) when the shape has no fused variant
 static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
@@ -348,7 +349,7 @@ static int fused_launch(const float* U, const int64_t* uid, int64_t n_users, con
     }();
     if (which == 0) {
         const int rc = b2r_bprmf_flash_launch(U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, qout, B, C,
-                                              d, err_flag, loss_out, done_counter, stream);
+                                              d, err_flag, loss_out, done_counter, nullptr, nullptr, stream);
         if (rc != B2R_E_UNSUPPORTED) return rc;
     }
     if (which == 2 && d == 64 && C <= 104)

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "plan_direct.cuh"
 
 extern "C" int b2r_bprmf_fused_fwd_bwd(const float* U, const int64_t* uid, int64_t n_users, const float* I,
                                        const int64_t* iid, int64_t n_items, float* pred, float* grad_pred,
@@ -21,6 +22,11 @@ int b2r_bprmf_fused_fwd_bwd_loss(const float* U, const int64_t* uid, int64_t n_u
                                  int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter,
                                  b2r_stream_t stream);
 
+int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, const float* I, const int64_t* iid,
+                           int64_t n_items, float* pred, float* grad_pred, float* row_loss, float* dQ, float* qout,
+                           int B, int C, int d, int32_t* err_flag, float* loss_out, unsigned int* done_counter,
+                           const b2r::DirectPlanDev* plan_i, const b2r::DirectPlanDev* plan_u, b2r_stream_t stream);
+
 namespace b2r {
 
 struct PlanBuf {
@@ -31,6 +37,7 @@ struct StepLayout {
     size_t q, pred, g, rows, dQ, counter;
     PlanBuf plan[2];
     size_t iws_bytes, uws_bytes;
+    size_t dir_i, dir_u, dir_i_bytes, dir_u_bytes;       // direct plans (plan_direct.cuh); 0 bytes: not available
     size_t total;
 };
 
@@ -54,6 +61,11 @@ static bool step_layout(int B, int C, int d, int64_t n_users, int64_t n_items, S
         L->plan[s].iws = take(L->iws_bytes);
         L->plan[s].uws = take(L->uws_bytes);
     }
+    L->dir_i_bytes = direct_workspace_bytes((int64_t)n, n_items);
+    L->dir_u_bytes = direct_workspace_bytes(B, n_users);
+    if (L->dir_i_bytes == 0 || L->dir_u_bytes == 0) L->dir_i_bytes = L->dir_u_bytes = 0;
+    L->dir_i = take(L->dir_i_bytes);
+    L->dir_u = take(L->dir_u_bytes);
     L->total = off;
     return L->iws_bytes != 0 && L->uws_bytes != 0;
 }
@@ -69,6 +81,7 @@ struct StepCtx {
     const void* pre_uid;
     const void* pre_iid;
     bool have_pre;
+    bool direct;                      // the forward kernel fills the index plans itself (no side stream, no prefetch)
 };
 
 }  // namespace b2r
@@ -123,6 +136,19 @@ extern "C" int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t
     for (int sl = 0; sl < 2; ++sl) {      // bucket counters start at zero (the scan kernel re-zeroes them every step)
         int rc = b2r_bucket_workspace_init(c->ws + c->L.plan[sl].iws, c->L.iws_bytes, (int64_t)B * C, n_items, c->side);
         if (rc == 0) rc = b2r_bucket_workspace_init(c->ws + c->L.plan[sl].uws, c->L.uws_bytes, B, n_users, c->side);
+        if (rc != 0) {
+            delete c;
+            return rc;
+        }
+    }
+    // Default step: the forward kernel drops the (row, position) pairs into the plans as it reads the ids and one sort
+    // kernel follows (plan_direct.cuh).  B2R_STEP=prefetch selects the earlier form -- count / scan / scatter / sort of
+    // the NEXT batch on a high-priority side stream underneath this step's kernels -- for A/B runs.
+    const char* mode = getenv("B2R_STEP");
+    c->direct = c->L.dir_i_bytes != 0 && !(mode && mode[0] == 'p');
+    if (c->direct) {
+        int rc = direct_workspace_init(c->ws + c->L.dir_i, c->L.dir_i_bytes, (int64_t)B * C, n_items, c->side);
+        if (rc == 0) rc = direct_workspace_init(c->ws + c->L.dir_u, c->L.dir_u_bytes, B, n_users, c->side);
         if (rc != 0) {
             delete c;
             return rc;
@@ -187,6 +213,34 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
     cudaStream_t main_s = as_stream(stream);
     const int64_t n = (int64_t)B * C;
     int rc;
+
+    if (c->direct) {
+        // forward (+ plan pairs) -> per-bucket sort of both plans -> update of both tables: three launches, one stream
+        float* q = reinterpret_cast<float*>(base + c->L.q);
+        const DirectPlanDev pi = direct_plan_dev(base + c->L.dir_i, n, c->n_items);
+        const DirectPlanDev pu = direct_plan_dev(base + c->L.dir_u, B, c->n_users);
+        profile_begin(B2R_PROF_SCORE_FWD, main_s);
+        rc = b2r_bprmf_flash_launch(t->U, uid, t->n_users, t->I, iid, t->n_items, nullptr, g, rows, dQ, q, B, C, d, err_flag,
+                                    loss_out, reinterpret_cast<unsigned int*>(base + c->L.counter), &pi, &pu, main_s);
+        if (rc == 0) {
+            profile_end(B2R_PROF_SCORE_FWD, main_s);
+            profile_begin(B2R_PROF_PLAN_I, main_s);
+            rc = direct_sort_pair(base + c->L.dir_i, n, c->n_items, base + c->L.dir_u, B, c->n_users, main_s);
+            if (rc != 0) return rc;
+            profile_end(B2R_PROF_PLAN_I, main_s);
+            const b2r_grad_source su{dQ, nullptr, nullptr, B, 1, 0};
+            const b2r_grad_source si{q, g, nullptr, n, C, 0};
+            const b2r_apply_job ji{base + c->L.dir_i, n, t->n_items, &si, nullptr, nullptr, t->I, t->Im, t->Iv};
+            const b2r_apply_job ju{base + c->L.dir_u, B, t->n_users, &su, nullptr, nullptr, t->U, t->Um, t->Uv};
+            profile_begin(B2R_PROF_SEGMENT_I, main_s);
+            rc = direct_apply_pair(&ji, &ju, d, 2, opt, main_s);
+            if (rc != 0) return rc;
+            profile_end(B2R_PROF_SEGMENT_I, main_s);
+            return 0;
+        }
+        if (rc != B2R_E_UNSUPPORTED) return rc;
+        c->direct = false;                                  // shape outside the streaming kernel's class: prefetch form
+    }
 
     // everything the side stream does from here on is ordered after what main has enqueued so far
     // (in particular after the previous step's readers of the plan buffer about to be overwritten)

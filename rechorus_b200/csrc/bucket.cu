@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "plan_direct.cuh"
 
 namespace b2r {
 
@@ -351,6 +352,61 @@ __device__ __forceinline__ bool bucket_sort_counting(uint64_t* __restrict__ g, i
     return true;
 }
 
+// sort one bucket's pairs g[0, cnt) in place (beg = index of g[0] in the plan's pair address space, tg = scratch of the
+// same extent for the merge path) and list its row heads / long rows
+template <bool COUNT>
+__device__ __forceinline__ void sort_one_bucket(uint64_t* g, uint64_t* tg, int cnt, int beg, uint32_t row0, int shift,
+                                                uint64_t* s, int* hist, int* scratch, int* head_cnt, int* head_base,
+                                                int* n_long, uint2* longs, int long_cap, int* n_heads, uint4* heads) {
+    const int tid = threadIdx.x;
+    if (COUNT && cnt <= kCap && shift <= kCountShift &&
+        bucket_sort_counting(g, cnt, beg, row0, 1 << shift, s, hist, scratch, n_heads, heads))
+        return;
+    if (cnt <= kCap) {
+        int P = 32;
+        while (P < cnt) P <<= 1;
+        for (int i = tid; i < P; i += kBT) s[i] = i < cnt ? g[i] : ~0ull;
+        __syncthreads();
+        bitonic_sort_smem(s, P);
+        for (int i = tid; i < cnt; i += kBT) g[i] = s[i];
+        emit_row_heads(s, cnt, beg, n_long, longs, long_cap, n_heads, heads, head_cnt, head_base);
+    } else {
+        // chunked shared-memory sorts ...
+        for (int c0 = 0; c0 < cnt; c0 += kCap) {
+            const int m = min(kCap, cnt - c0);
+            int P = 32;
+            while (P < m) P <<= 1;
+            for (int i = tid; i < P; i += kBT) s[i] = i < m ? g[c0 + i] : ~0ull;
+            __syncthreads();
+            bitonic_sort_smem(s, P);
+            for (int i = tid; i < m; i += kBT) g[c0 + i] = s[i];
+            __syncthreads();
+        }
+        // ... then pairwise merges by rank (each element: own index + rank in the sibling run), ping-pong g <-> tg
+        uint64_t* src = g;
+        uint64_t* dst = tg;
+        for (int width = kCap; width < cnt; width <<= 1) {
+            for (int i = tid; i < cnt; i += kBT) {
+                const int run = i / width;
+                const int base = (run & ~1) * width;
+                const int a0 = base, a1 = min(cnt, base + width), b1 = min(cnt, base + 2 * width);
+                const uint64_t v = src[i];
+                int pos;
+                if ((run & 1) == 0) pos = (i - a0) + lower_bound64(src + a1, b1 - a1, v);
+                else pos = (i - a1) + lower_bound64(src + a0, a1 - a0, v);
+                dst[base + pos] = v;
+            }
+            __syncthreads();
+            uint64_t* t2 = src; src = dst; dst = t2;
+        }
+        if (src != g) {
+            for (int i = tid; i < cnt; i += kBT) g[i] = src[i];
+            __syncthreads();
+        }
+        emit_row_heads(g, cnt, beg, n_long, longs, long_cap, n_heads, heads, head_cnt, head_base);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // k_bucket_sort: one CTA per bucket sorts its (row, position) pairs in place.  Buckets cover ascending, disjoint
 // row ranges, so afterwards the whole pairs array is sorted by (row, position) -- the same order a device-wide
@@ -367,61 +423,99 @@ k_bucket_sort(uint64_t* __restrict__ pairs, uint64_t* __restrict__ tmp, const in
     __shared__ int head_cnt, head_base;
     __shared__ int hist[COUNT ? kCountRows + 1 : 1];
     __shared__ int scratch[COUNT ? 40 : 1];
-    const int tid = threadIdx.x;
-    if (tid == 0) head_cnt = 0;
+    if (threadIdx.x == 0) head_cnt = 0;
     __syncthreads();
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
         const int beg = off[b];
         const int cnt = off[b + 1] - beg;
         if (cnt == 0) continue;
-        uint64_t* g = pairs + beg;
-        if (COUNT && cnt <= kCap && shift <= kCountShift &&
-            bucket_sort_counting(g, cnt, beg, (uint32_t)b << shift, 1 << shift, s, hist, scratch, n_heads, heads))
-            continue;
-        if (cnt <= kCap) {
-            int P = 32;
-            while (P < cnt) P <<= 1;
-            for (int i = tid; i < P; i += kBT) s[i] = i < cnt ? g[i] : ~0ull;
-            __syncthreads();
-            bitonic_sort_smem(s, P);
-            for (int i = tid; i < cnt; i += kBT) g[i] = s[i];
-            emit_row_heads(s, cnt, beg, n_long, longs, long_cap, n_heads, heads, &head_cnt, &head_base);
-        } else {
-            // chunked shared-memory sorts ...
-            for (int c0 = 0; c0 < cnt; c0 += kCap) {
-                const int m = min(kCap, cnt - c0);
-                int P = 32;
-                while (P < m) P <<= 1;
-                for (int i = tid; i < P; i += kBT) s[i] = i < m ? g[c0 + i] : ~0ull;
-                __syncthreads();
-                bitonic_sort_smem(s, P);
-                for (int i = tid; i < m; i += kBT) g[c0 + i] = s[i];
-                __syncthreads();
-            }
-            // ... then pairwise merges by rank (each element: own index + rank in the sibling run), ping-pong g <-> t
-            uint64_t* src = g;
-            uint64_t* dst = tmp + beg;
-            for (int width = kCap; width < cnt; width <<= 1) {
-                for (int i = tid; i < cnt; i += kBT) {
-                    const int run = i / width;
-                    const int base = (run & ~1) * width;
-                    const int a0 = base, a1 = min(cnt, base + width), b1 = min(cnt, base + 2 * width);
-                    const uint64_t v = src[i];
-                    int pos;
-                    if ((run & 1) == 0) pos = (i - a0) + lower_bound64(src + a1, b1 - a1, v);
-                    else pos = (i - a1) + lower_bound64(src + a0, a1 - a0, v);
-                    dst[base + pos] = v;
-                }
-                __syncthreads();
-                uint64_t* t2 = src; src = dst; dst = t2;
-            }
-            if (src != g) {
-                for (int i = tid; i < cnt; i += kBT) g[i] = src[i];
-                __syncthreads();
-            }
-            emit_row_heads(g, cnt, beg, n_long, longs, long_cap, n_heads, heads, &head_cnt, &head_base);
-        }
+        sort_one_bucket<COUNT>(pairs + beg, tmp + beg, cnt, beg, (uint32_t)b << shift, shift, s, hist, scratch, &head_cnt,
+                               &head_base, n_long, longs, long_cap, n_heads, heads);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_bucket_sort_direct: the same per-bucket sort over plans whose pairs were dropped into fixed-capacity bucket regions
+// by the forward kernel (plan_direct.cuh).  A bucket that overflowed its region (skewed ids) first collects its spilled
+// pairs from the spill list into the "big" area behind the regions and is sorted there.  Cursors are left zero for the
+// next step.  Two plans (two tables of one step) ride in one launch.
+// ---------------------------------------------------------------------------------------------------
+struct DirectSortJob {
+    int nb, cap, shift, grid;
+    int* cursor;
+    uint64_t* region;
+    uint64_t* spill;
+    int* counters;               // [0] spill count, [1] big cursor, [2] n_long, [3] n_heads
+    int spill_cap;
+    uint64_t* big;
+    uint64_t* tmp;               // scratch for the merge path, same extent as big
+    int big_cap;
+    uint2* longs;
+    int long_cap;
+    uint4* heads;
+};
+
+template <bool COUNT>
+__device__ __forceinline__ void direct_sort_job(const DirectSortJob& J, int bid, uint64_t* s, int* hist, int* scratch,
+                                                int* head_cnt, int* head_base, int* sh) {
+    const int tid = threadIdx.x;
+    for (int b = bid; b < J.nb; b += J.grid) {
+        if (tid == 0) {
+            sh[0] = J.cursor[(int64_t)b * kPadD];
+            J.cursor[(int64_t)b * kPadD] = 0;
+        }
+        __syncthreads();
+        const int raw = sh[0];
+        __syncthreads();
+        if (raw == 0) continue;
+        const uint32_t row0 = (uint32_t)b << J.shift;
+        if (raw <= J.cap) {
+            const int beg = b * J.cap;
+            sort_one_bucket<COUNT>(J.region + (int64_t)beg, J.tmp, raw, beg, row0, J.shift, s, hist, scratch, head_cnt,
+                                   head_base, J.counters + 2, J.longs, J.long_cap, J.counters + 3, J.heads);
+            continue;
+        }
+        // overflow: region (cap pairs) + this bucket's share of the spill list -> contiguous run in the big area
+        const int nsp = min(J.counters[0], J.spill_cap);
+        int mine = 0;
+        for (int i = tid; i < nsp; i += kBT) mine += ((uint32_t)(J.spill[i] >> 32) >> J.shift) == (uint32_t)b ? 1 : 0;
+        if (tid == 0) sh[1] = 0;
+        __syncthreads();
+        if (mine) atomicAdd(&sh[1], mine);
+        __syncthreads();
+        const int total = J.cap + sh[1];
+        if (tid == 0) {
+            sh[2] = atomicAdd(&J.counters[1], total);
+            sh[3] = 0;
+        }
+        __syncthreads();
+        const int base = sh[2];
+        if (base + total > J.big_cap) continue;             // cannot happen (big_cap = 2n); never write out of bounds
+        uint64_t* g = J.big + base;
+        for (int i = tid; i < J.cap; i += kBT) g[i] = J.region[(int64_t)b * J.cap + i];
+        for (int i = tid; i < nsp; i += kBT) {
+            const uint64_t v = J.spill[i];
+            if (((uint32_t)(v >> 32) >> J.shift) == (uint32_t)b) g[J.cap + atomicAdd(&sh[3], 1)] = v;
+        }
+        __syncthreads();
+        // pair indices of the big area continue after the regions: nb * cap + offset
+        sort_one_bucket<COUNT>(g, J.tmp + base, total, J.nb * J.cap + base, row0, J.shift, s, hist, scratch, head_cnt,
+                               head_base, J.counters + 2, J.longs, J.long_cap, J.counters + 3, J.heads);
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBT)
+k_bucket_sort_direct(const __grid_constant__ DirectSortJob a, const __grid_constant__ DirectSortJob b) {
+    __shared__ uint64_t s[kCap];
+    __shared__ int head_cnt, head_base;
+    __shared__ int hist[COUNT ? kCountRows + 1 : 1];
+    __shared__ int scratch[COUNT ? 40 : 1];
+    __shared__ int sh[4];
+    if (threadIdx.x == 0) head_cnt = 0;
+    __syncthreads();
+    if ((int)blockIdx.x < a.grid) direct_sort_job<COUNT>(a, (int)blockIdx.x, s, hist, scratch, &head_cnt, &head_base, sh);
+    else direct_sort_job<COUNT>(b, (int)blockIdx.x - a.grid, s, hist, scratch, &head_cnt, &head_base, sh);
 }
 
 // One table's share of an apply launch: the sorted pairs and row heads of its plan, its contribution sources and
@@ -439,6 +533,7 @@ struct ApplyJob {
     float* M;
     float* V;
     float* dense;
+    int* reset;                  // direct plans: the spill counter, zeroed here for the next step (NULL otherwise)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -457,6 +552,7 @@ __device__ __forceinline__ void apply_job(const ApplyJob& J, const OptK& opt, in
     const int sub = threadIdx.x % LPR, grp = threadIdx.x / LPR;
     const int sld = opt.state_ld ? opt.state_ld : D;
     const int n_heads = *J.n_heads;
+    if (J.reset != nullptr && bid == 0 && threadIdx.x == 0) *J.reset = 0;
     for (int h = bid * GPC + grp; h < n_heads; h += J.grid * GPC) {
         const uint4 e = __ldg(J.heads + h);
         const int len = (int)e.w;
@@ -681,6 +777,7 @@ static int make_job(const b2r_apply_job* j, int d, int mode, const b2r_optim& o,
     out->s0 = to_bsrc(j->s0, d);
     out->s1 = to_bsrc(j->s1, d);
     out->W = j->W; out->M = j->m; out->V = j->v; out->dense = j->dense;
+    out->reset = nullptr;
     const int gpc = kBT / (d / 4);
     int64_t need = (j->n + gpc - 1) / gpc;
     if (need > grid_cap) need = grid_cap;
@@ -688,8 +785,24 @@ static int make_job(const b2r_apply_job* j, int d, int mode, const b2r_optim& o,
     return 0;
 }
 
+static int apply_pair_common(const b2r_apply_job* ja, const b2r_apply_job* jb, int d, int mode, const b2r_optim* opt,
+                             cudaStream_t s, bool direct);
+
 extern "C" int b2r_bucket_apply_pair(const b2r_apply_job* ja, const b2r_apply_job* jb, int d, int mode,
                                      const b2r_optim* opt, b2r_stream_t stream) {
+    return apply_pair_common(ja, jb, d, mode, opt, as_stream(stream), false);
+}
+
+namespace b2r {
+int direct_apply_pair(const b2r_apply_job* ja, const b2r_apply_job* jb, int d, int mode, const b2r_optim* opt, cudaStream_t s) {
+    return apply_pair_common(ja, jb, d, mode, opt, s, true);
+}
+}  // namespace b2r
+
+static int make_job_direct(const b2r_apply_job* j, int d, int mode, const b2r_optim& o, int grid_cap, ApplyJob* out);
+
+static int apply_pair_common(const b2r_apply_job* ja, const b2r_apply_job* jb, int d, int mode, const b2r_optim* opt,
+                             cudaStream_t s, bool direct) {
     B2R_REQUIRE(ja, B2R_E_BADARG, "b2r_bucket_apply: null job");
     B2R_REQUIRE(d == 32 || d == 64 || d == 128, B2R_E_UNSUPPORTED, "b2r_bucket_apply: d=%d (have 32, 64, 128)", d);
     B2R_REQUIRE(mode == 1 || mode == 2, B2R_E_BADARG, "b2r_bucket_apply: mode %d (1 = dense +=, 2 = optimizer)", mode);
@@ -701,18 +814,17 @@ extern "C" int b2r_bucket_apply_pair(const b2r_apply_job* ja, const b2r_apply_jo
     }
     ApplyJob a{}, b{};
     const int cap = sm_count() * 16;             // ~2.7 waves of 6 resident CTAs/SM; x12 and x20 measured slower
-    int rc = make_job(ja, d, mode, o, cap, &a);
+    int rc = direct ? make_job_direct(ja, d, mode, o, cap, &a) : make_job(ja, d, mode, o, cap, &a);
     if (rc != 0) return rc;
     if (jb != nullptr) {
         // the second job is the small one by convention; its CTAs come first in the grid so that they are placed at once
-        rc = make_job(jb, d, mode, o, cap, &b);
+        rc = direct ? make_job_direct(jb, d, mode, o, cap, &b) : make_job(jb, d, mode, o, cap, &b);
         if (rc != 0) return rc;
     } else {
         b = a;
         b.grid = 0;
     }
     const OptK ok = make_optk(o);
-    cudaStream_t s = as_stream(stream);
     const int grid = a.grid + b.grid;
 #define B2R_BK(LPR, MODE) k_apply_sorted<LPR, MODE><<<grid, kBT, 0, s>>>(b.grid ? b : a, b.grid ? a : b, ok)
     if (mode == 1) {
@@ -730,4 +842,150 @@ extern "C" int b2r_bucket_apply(const void* ws, int64_t n, int64_t n_rows, int d
                                 const b2r_optim* opt, b2r_stream_t stream) {
     const b2r_apply_job j{ws, n, n_rows, s0, s1, dense, W, m, v};
     return b2r_bucket_apply_pair(&j, nullptr, d, mode, opt, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// direct plans (plan_direct.cuh): layout, init, the producer's view, the sort launch, the apply job
+// ---------------------------------------------------------------------------------------------------
+namespace b2r {
+
+struct DirectLayout {
+    size_t cursor, region, big, tmp, spill, counters, longs, heads, total;
+    int nb, shift, cap, big_cap, spill_cap, long_cap;
+};
+
+static DirectLayout direct_layout(int64_t n, int64_t n_rows) {
+    const BucketGeom g = bucket_geom(n, n_rows);
+    DirectLayout L;
+    L.nb = g.nb;
+    L.shift = g.shift;
+    // region capacity: 3x the uniform share + slack, a multiple of 64, at most what one shared-memory sort takes;
+    // more skew than that goes through the spill list
+    int64_t cap = (3 * (n / (g.nb > 0 ? g.nb : 1)) + 64 + 63) / 64 * 64;
+    if (cap < 128) cap = 128;
+    if (cap > kCap) cap = kCap;
+    L.cap = (int)cap;
+    L.big_cap = (int)(2 * n);
+    L.spill_cap = (int)n;
+    L.long_cap = (int)(n / kLong + 1);
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += align_up(bytes, 256);
+        return r;
+    };
+    L.cursor = take((size_t)L.nb * 4 * kPadD);
+    L.counters = take(256);
+    L.region = take((size_t)L.nb * L.cap * 8);
+    L.big = take((size_t)L.big_cap * 8);                   // directly behind the regions: one pair address space
+    L.tmp = take((size_t)L.big_cap * 8);
+    L.spill = take((size_t)L.spill_cap * 8);
+    L.longs = take((size_t)L.long_cap * 8);
+    L.heads = take((size_t)n * 16);
+    L.total = o;
+    return L;
+}
+
+static bool direct_ok(int64_t n, int64_t n_rows) {
+    if (n <= 0 || n > 0x3fffffff || n_rows <= 0 || n_rows >= 0xffffffffLL) return false;
+    const DirectLayout L = direct_layout(n, n_rows);
+    return (int64_t)L.nb * L.cap + L.big_cap < 0x7fffffffLL && L.big == L.region + align_up((size_t)L.nb * L.cap * 8, 256)
+           && ((size_t)L.nb * L.cap * 8) % 256 == 0;     // big must start exactly at pair index nb * cap
+}
+
+size_t direct_workspace_bytes(int64_t n, int64_t n_rows) {
+    return direct_ok(n, n_rows) ? direct_layout(n, n_rows).total : 0;
+}
+
+int direct_workspace_init(void* ws, size_t ws_bytes, int64_t n, int64_t n_rows, cudaStream_t s) {
+    B2R_REQUIRE(ws && direct_ok(n, n_rows), B2R_E_UNSUPPORTED, "direct plan: n=%lld n_rows=%lld unsupported", (long long)n,
+                (long long)n_rows);
+    const DirectLayout L = direct_layout(n, n_rows);
+    B2R_REQUIRE(ws_bytes >= L.total, B2R_E_WORKSPACE, "direct plan: workspace %zu < %zu", ws_bytes, L.total);
+    B2R_CUDA_OK(cudaMemsetAsync(static_cast<char*>(ws) + L.cursor, 0, L.region - L.cursor, s));   // cursors + counters
+    return 0;
+}
+
+DirectPlanDev direct_plan_dev(void* ws, int64_t n, int64_t n_rows) {
+    const DirectLayout L = direct_layout(n, n_rows);
+    char* base = static_cast<char*>(ws);
+    DirectPlanDev P;
+    P.cursor = reinterpret_cast<int*>(base + L.cursor);
+    P.region = reinterpret_cast<uint64_t*>(base + L.region);
+    P.spill = reinterpret_cast<uint64_t*>(base + L.spill);
+    P.counters = reinterpret_cast<int*>(base + L.counters);
+    P.cap = L.cap;
+    P.shift = L.shift;
+    P.spill_cap = L.spill_cap;
+    return P;
+}
+
+static DirectSortJob direct_sort_job_of(void* ws, int64_t n, int64_t n_rows, int grid_cap) {
+    const DirectLayout L = direct_layout(n, n_rows);
+    char* base = static_cast<char*>(ws);
+    DirectSortJob J;
+    J.nb = L.nb; J.cap = L.cap; J.shift = L.shift;
+    J.grid = L.nb < grid_cap ? L.nb : grid_cap;
+    J.cursor = reinterpret_cast<int*>(base + L.cursor);
+    J.region = reinterpret_cast<uint64_t*>(base + L.region);
+    J.spill = reinterpret_cast<uint64_t*>(base + L.spill);
+    J.counters = reinterpret_cast<int*>(base + L.counters);
+    J.spill_cap = L.spill_cap;
+    J.big = reinterpret_cast<uint64_t*>(base + L.big);
+    J.tmp = reinterpret_cast<uint64_t*>(base + L.tmp);
+    J.big_cap = L.big_cap;
+    J.longs = reinterpret_cast<uint2*>(base + L.longs);
+    J.long_cap = L.long_cap;
+    J.heads = reinterpret_cast<uint4*>(base + L.heads);
+    return J;
+}
+
+int direct_sort_pair(void* ws_a, int64_t n_a, int64_t rows_a, void* ws_b, int64_t n_b, int64_t rows_b, cudaStream_t s) {
+    B2R_REQUIRE(ws_a && direct_ok(n_a, rows_a), B2R_E_BADARG, "direct_sort_pair: bad plan a");
+    const int cap = sm_count() * 8;
+    DirectSortJob a = direct_sort_job_of(ws_a, n_a, rows_a, cap), b = a;
+    b.grid = 0;
+    if (ws_b != nullptr) {
+        B2R_REQUIRE(direct_ok(n_b, rows_b), B2R_E_BADARG, "direct_sort_pair: bad plan b");
+        b = direct_sort_job_of(ws_b, n_b, rows_b, cap);
+    }
+    // the small plan's CTAs first (they are placed at once), like k_apply_sorted's two jobs
+    if (b.grid) k_bucket_sort_direct<true><<<a.grid + b.grid, kBT, 0, s>>>(b, a);
+    else k_bucket_sort_direct<true><<<a.grid, kBT, 0, s>>>(a, b);
+    B2R_LAUNCH_OK("k_bucket_sort_direct");
+    return 0;
+}
+
+}  // namespace b2r
+
+static int make_job_direct(const b2r_apply_job* j, int d, int mode, const b2r_optim& o, int grid_cap, ApplyJob* out) {
+    B2R_REQUIRE(j->ws && j->s0 && j->s0->src, B2R_E_BADARG, "direct apply: null pointer");
+    B2R_REQUIRE(j->s0->n + (j->s1 ? j->s1->n : 0) == j->n, B2R_E_BADARG, "direct apply: sources do not cover the plan");
+    if (mode == 1) {
+        B2R_REQUIRE(j->dense, B2R_E_BADARG, "direct apply: mode 1 needs dense");
+    } else {
+        B2R_REQUIRE(j->W, B2R_E_BADARG, "direct apply: mode 2 needs W");
+        B2R_REQUIRE(o.kind != 1 || (j->m && j->v), B2R_E_BADARG, "direct apply: Adam needs m and v");
+        B2R_REQUIRE(o.kind != 2 || j->v, B2R_E_BADARG, "direct apply: Adagrad needs v");
+    }
+    B2R_REQUIRE(direct_ok(j->n, j->n_rows), B2R_E_UNSUPPORTED, "direct apply: n=%lld n_rows=%lld unsupported",
+                (long long)j->n, (long long)j->n_rows);
+    const DirectLayout L = direct_layout(j->n, j->n_rows);
+    const char* base = static_cast<const char*>(j->ws);
+    int* counters = reinterpret_cast<int*>(const_cast<char*>(base) + L.counters);
+    out->pairs = reinterpret_cast<const uint64_t*>(base + L.region);       // regions, then the big area: one index space
+    out->heads = reinterpret_cast<const uint4*>(base + L.heads);
+    out->n_heads = counters + 3;
+    out->n_long = counters + 2;
+    out->longs = reinterpret_cast<const uint2*>(base + L.longs);
+    out->long_cap = L.long_cap;
+    out->s0 = to_bsrc(j->s0, d);
+    out->s1 = to_bsrc(j->s1, d);
+    out->W = j->W; out->M = j->m; out->V = j->v; out->dense = j->dense;
+    out->reset = counters;                                                  // spill count -> 0 for the next step
+    const int gpc = kBT / (d / 4);
+    int64_t need = (j->n + gpc - 1) / gpc;
+    if (need > grid_cap) need = grid_cap;
+    out->grid = (int)(need < 1 ? 1 : need);
+    return 0;
 }

@@ -225,7 +225,7 @@ class BaseRunner:
         reproduced (a sequential NumPy / torch CPU stream cannot be drawn in parallel); results are reproducible from
         (seed, epoch)."""
         model = dataset.model
-        if "history_items" in dataset._get_feed_dict(0):
+        if hasattr(model, "history_max"):
             raise ValueError("fit_on_device: sequential datasets are not supported (history collate is host-side)")
         if model.optimizer is None:
             model.optimizer = self._build_optimizer(model)

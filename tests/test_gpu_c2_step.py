@@ -135,7 +135,10 @@ def test_train_step_full_size_three_prefetched_steps_match_lazy_adam_on_oracle_g
         assert abs(float(loss) - loss_o) <= 1e-5
         for name, (w0, m0, v0), g, W, e, idx in (("U", before[0:3], gU, U, eu, uud), ("I", before[3:6], gI, I, ei, uid_d)):
             w1, m1, v1 = _lazy_adam(w0, m0, v0, g, t)
-            assert (W[idx].cpu().double() - w1).abs().max() <= 1e-6, (name, t)
+            err = (W[idx].cpu().double() - w1).abs()
+            well = g.abs() > 1e-7                 # Adam divides by |g| + 1e-8: entries with |g| near eps amplify rounding
+            assert float(err[well].max()) <= 1e-6, (name, t, float(err[well].max()))
+            assert float(err.max()) <= 5e-5, (name, t, float(err.max()))     # ill-conditioned entries: a fraction of lr
             assert (e["m"][idx].cpu().double() - m1).abs().max() <= 1e-5 * float(g.abs().max()) + 1e-12, (name, t)
             assert (e["v"][idx].cpu().double() - v1).abs().max() <= 1e-4 * float(v1.abs().max()) + 1e-16, (name, t)
             # the step must be reproduced, not lost: the update itself to 1 % of its own size (lr) on well-conditioned
@@ -175,3 +178,44 @@ def test_contract_route_equals_train_step_at_full_size():
         assert abs(float(la) - float(lb)) <= 2e-6
     for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert (pa - pb).abs().max() <= 1e-6, k
+
+
+@pytest.mark.parametrize("kind", ["one_row", "two_hot_buckets"])
+def test_train_step_degenerate_id_distributions_match_oracle(kind):
+    """skew the fixed-capacity bucket regions of the step's index plan cannot hold: every pair on ONE row (one bucket
+    receives the whole batch through the spill list and is merge-sorted in chunks) / two hot buckets plus uniform rest"""
+    from rechorus_b200 import ops
+    Bs = 1024
+    g = torch.Generator().manual_seed(77)
+    uid = torch.randint(1, N_USERS, (Bs,), generator=g)
+    iid = torch.randint(1, N_ITEMS, (Bs, C), generator=g)
+    if kind == "one_row":
+        iid[:] = 7
+        uid[:] = 3
+    else:
+        iid[:, ::3] = torch.randint(1000, 1400, (Bs, (C + 2) // 3), generator=g)          # ~34k pairs in one 512-row bucket
+        iid[:, 1::7] = torch.randint(900_000, 900_003, (Bs, len(range(1, C, 7))), generator=g)   # three very long rows
+        uid[::2] = torch.randint(5000, 5040, (Bs // 2,), generator=g)                    # hot users
+    f = {"user_id": uid.to(_dev()), "item_id": iid.to(_dev()), "batch_size": Bs, "phase": "train"}
+    m = _model()
+    U, I = m.u_embeddings.weight.data, m.i_embeddings.weight.data
+    eu, ei = m.optimizer.entry(m.u_embeddings.weight), m.optimizer.entry(m.i_embeddings.weight)
+    for t in (1, 2):
+        uu, ui = torch.unique(uid), torch.unique(iid)
+        uud, uid_d = uu.to(_dev()), ui.to(_dev())
+        before = [x[idx].cpu() for x, idx in ((U, uud), (eu["m"], uud), (eu["v"], uud), (I, uid_d), (ei["m"], uid_d),
+                                              (ei["v"], uid_d))]
+        loss = m.train_step(f)
+        torch.cuda.synchronize()
+        _, loss_o, gU, gI = _compact_oracle_grads(before[0], before[3], uu, ui, uid, iid)
+        assert abs(float(loss) - loss_o) <= 1e-5
+        for name, (w0, m0, v0), gr, W, idx in (("U", before[0:3], gU, U, uud), ("I", before[3:6], gI, I, uid_d)):
+            w1, _, _ = _lazy_adam(w0, m0, v0, gr, t)
+            ok = gr.abs() > 1e-6
+            assert ((W[idx].cpu().double() - w1).abs()[ok]).max() <= 2e-6, (kind, name, t)
+    ops.check_ids()
+    m2 = _model()                                             # and the same bits on a second run
+    for t in (1, 2):
+        m2.train_step(f)
+    torch.cuda.synchronize()
+    assert torch.equal(m2.i_embeddings.weight.data, I) and torch.equal(m2.u_embeddings.weight.data, U)

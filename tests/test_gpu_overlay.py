@@ -113,26 +113,35 @@ def test_deep_models_through_unchanged_main_track_reference_cpu_run(workdir, mod
     # Adam amplifies rounding-level gradient entries to lr-sized steps (see test_gpu_zz_fit_golden.py): the bulk of the
     # parameters agrees closely, the tail is bounded by the step budget lr * steps
     dev = torch.cat([(w_gpu[k] - w_ref[k]).abs().reshape(-1) for k in w_ref])
-    assert float(dev.median()) <= 2e-4 and float(dev.max()) <= 0.01 * 2 * 12
+    # NeuMF starts on a flat loss surface (loss stays at ln 2): nearly every gradient entry is rounding-level, and the
+    # reference's own fp32 run sits ~1e-2 (90th percentile) from its fp64 run (tests/golden/fit_neumf.npz "w1_64:")
+    med_tol = 2e-4 if model == "SASRec" else 5e-3
+    assert float(dev.median()) <= med_tol and float(dev.max()) <= 0.01 * 2 * 12, (float(dev.median()), float(dev.max()))
     for k in m_ref:
         assert abs(m_gpu[k] - m_ref[k]) <= 0.1, (k, m_gpu[k], m_ref[k])
 
 
-def test_out_of_range_id_raises_like_the_reference(workdir):
-    """a corpus whose dev file names an item beyond n_items: ATen raises IndexError in the reference (BPRMF.py:39-40);
-    the kernels clamp + count and the model raises when the runner switches phase"""
-    tmp = os.path.join(workdir, "bad")
-    os.makedirs(tmp)
-    path = _dataset(tmp)
-    dev = pd.read_csv(os.path.join(path, "tiny", "dev.csv"), sep="\t")
-    # BaseReader sizes n_items from max(item_id) over train/dev/test: the NEGATIVES are not counted, so an oversized
-    # negative id is out of range for the tables
-    dev.loc[0, "neg_items"] = str([N_ITEMS + 50] * N_NEG)
-    dev.to_csv(os.path.join(path, "tiny", "dev.csv"), sep="\t", index=False)
-    cwd = os.path.join(tmp, "run", "src")
-    os.makedirs(cwd)
-    cmd = [sys.executable, *OVERLAY, "--ref", REF, "--model_name", "BPRMF", "--dataset", "tiny", "--path", path, "--gpu", "0",
-           "--num_workers", "0", "--epoch", "1", "--emb_size", "64", "--model_path", os.path.join(tmp, "m.pt"),
-           "--log_file", os.path.join(tmp, "l.txt"), "--regenerate", "1", "--save_final_results", "0"]
-    res = subprocess.run(cmd, cwd=cwd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=600)
-    assert res.returncode != 0 and "IndexError" in (res.stdout + res.stderr), (res.stdout + res.stderr)[-2000:]
+def test_out_of_range_id_raises_like_the_reference():
+    """ATen raises IndexError inside the reference's forward (BPRMF.py:39-40).  The reference's own reader cannot hand such
+    an id to the model (BaseReader.py:55-59 sizes the tables from the data and asserts the negatives), so the check is
+    made on the class the overlay builds: the kernels clamp + count, and the model raises the same exception type at the
+    next phase switch every runner performs (model.eval() / model.train(), BaseRunner.py:179,231)."""
+    import argparse
+    import types
+    from rechorus_b200 import overlay
+    classes = overlay.install(REF)
+    cls = classes["BPRMF"]
+    p = argparse.ArgumentParser()
+    p = cls.parse_model_args(p)
+    a = p.parse_args(["--emb_size", "64"])
+    a.device, a.model_path = torch.device("cuda", 0), "/tmp/_b2r_oob.pt"
+    model = cls(a, types.SimpleNamespace(n_users=20, n_items=30)).to(a.device)
+    model.apply(model.init_weights)
+    model.train()
+    feed = {"user_id": torch.tensor([1, 2]).cuda(), "item_id": torch.tensor([[3, 4], [5, 99]]).cuda(), "batch_size": 2,
+            "phase": "train"}
+    out = model(feed)                                    # the kernel does not read out of bounds ...
+    assert torch.isfinite(out["prediction"]).all()
+    with pytest.raises(IndexError):                      # ... and the bad id surfaces as the reference's exception type
+        model.eval()
+    model.eval()                                         # counter was reset by the raise
