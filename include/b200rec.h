@@ -387,6 +387,36 @@ B2R_API int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const int
                          const int64_t* next_uid, const int64_t* next_iid, const b2r_optim* opt,
                          float* loss_out, int32_t* err_flag, b2r_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row-sharded tables (BASELINE config 5): the exchange done by kernels over peer-mapped memory (symmetric-memory
+ * buffers of the ranks of one box; NVLink loads / stores) instead of collectives between kernels.  No reference
+ * counterpart (the reference is single-device); contract: SURVEY.md 8(e).  Pointer tables are HOST arrays of W device
+ * pointers (W <= 16).  Ordering between ranks is the caller's (signal-pad barriers between the phases).
+ *
+ * b2r_route_ids: stable partition of one table's ids [B, C] by owner (id / rows_per): pair (b, c) goes to slot
+ *   s of its owner o, slots counted in (sample, candidate) order; written through peer_rows[o][s] = local row and
+ *   peer_q[o][s] = q_base + b (the row of the replicated query block); the unused tail of each region gets row -1;
+ *   slot_of[b*C + c] = o * cap + s; dest_total[o] = pairs sent to o; *overflow += 1 if some dest_total > cap.
+ * b2r_serve_rows: for every request e with req_rows[e] >= 0: row req_rows[e] of T is stored into row req_q[e] of EVERY
+ *   rank's block peer_dst[k] (gather + all-gather in one pass).
+ * b2r_scatter_f32_to_peers / b2r_scatter_rows_to_peers: val[i] * scale (resp. row i of src) -> peer_dst[slot_of[i] / cap]
+ *   at element (row) slot_of[i] % cap.
+ * b2r_sum_rows_from_peers: out[i] = sum_k peer_src[k][offset + i], k ascending (fixed order -> deterministic).
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API size_t b2r_route_workspace_bytes(int B, int W);
+B2R_API int b2r_route_ids(const int64_t* ids, int B, int C, int W, int64_t rows_per, int64_t n_rows,
+                          const void* const* peer_rows, const void* const* peer_q, int64_t q_base, int cap,
+                          int* slot_of, int* dest_total, int* overflow, void* ws, size_t ws_bytes, int32_t* err_flag,
+                          b2r_stream_t stream);
+B2R_API int b2r_serve_rows(const float* T, int64_t n_t, const int64_t* req_rows, const int64_t* req_q, int64_t n,
+                           const void* const* peer_dst, int W, int d, int32_t* err_flag, b2r_stream_t stream);
+B2R_API int b2r_scatter_f32_to_peers(const float* val, const int* slot_of, int64_t n, const void* const* peer_dst, int W,
+                                     int cap, float scale, b2r_stream_t stream);
+B2R_API int b2r_scatter_rows_to_peers(const float* src, const int* slot_of, int64_t n, const void* const* peer_dst, int W,
+                                      int cap, int d, b2r_stream_t stream);
+B2R_API int b2r_sum_rows_from_peers(const void* const* peer_src, int W, int64_t offset_floats, float* out,
+                                    int64_t n_floats, b2r_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

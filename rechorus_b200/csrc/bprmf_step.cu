@@ -37,7 +37,7 @@ struct StepLayout {
     size_t q, pred, g, rows, dQ, counter;
     PlanBuf plan[2];
     size_t iws_bytes, uws_bytes;
-    size_t dir_i, dir_u, dir_i_bytes, dir_u_bytes;       // direct plans (plan_direct.cuh); 0 bytes: not available
+    size_t dir_i[2], dir_u[2], dir_i_bytes, dir_u_bytes; // direct plans (plan_direct.cuh), double-buffered; 0: not available
     size_t total;
 };
 
@@ -64,8 +64,10 @@ static bool step_layout(int B, int C, int d, int64_t n_users, int64_t n_items, S
     L->dir_i_bytes = direct_workspace_bytes((int64_t)n, n_items);
     L->dir_u_bytes = direct_workspace_bytes(B, n_users);
     if (L->dir_i_bytes == 0 || L->dir_u_bytes == 0) L->dir_i_bytes = L->dir_u_bytes = 0;
-    L->dir_i = take(L->dir_i_bytes);
-    L->dir_u = take(L->dir_u_bytes);
+    for (int sl = 0; sl < 2; ++sl) {
+        L->dir_i[sl] = take(L->dir_i_bytes);
+        L->dir_u[sl] = take(L->dir_u_bytes);
+    }
     L->total = off;
     return L->iws_bytes != 0 && L->uws_bytes != 0;
 }
@@ -81,7 +83,9 @@ struct StepCtx {
     const void* pre_uid;
     const void* pre_iid;
     bool have_pre;
-    bool direct;                      // the forward kernel fills the index plans itself (no side stream, no prefetch)
+    int mode;                         // 0: direct plans built one batch ahead on the side stream (default);
+                                      // 1: the forward kernel fills the direct plans itself, one stream (B2R_STEP=inline);
+                                      // 2: count / scan / scatter / sort bucket plans one batch ahead (B2R_STEP=legacy)
 };
 
 }  // namespace b2r
@@ -141,17 +145,21 @@ extern "C" int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t
             return rc;
         }
     }
-    // Default step: the forward kernel drops the (row, position) pairs into the plans as it reads the ids and one sort
-    // kernel follows (plan_direct.cuh).  B2R_STEP=prefetch selects the earlier form -- count / scan / scatter / sort of
-    // the NEXT batch on a high-priority side stream underneath this step's kernels -- for A/B runs.
+    // Index plans.  Default (mode 0): "direct" plans (plan_direct.cuh: one scatter launch into fixed-capacity bucket regions,
+    // one sort launch, both tables per launch) built for the NEXT batch on the high-priority side stream underneath this
+    // step's kernels.  B2R_STEP=inline (mode 1): the forward kernel scatters the pairs itself, everything on one stream.
+    // B2R_STEP=legacy (mode 2): the round-1 form, count / scan / scatter / sort per table (8 launches) one batch ahead.
     const char* mode = getenv("B2R_STEP");
-    c->direct = c->L.dir_i_bytes != 0 && !(mode && mode[0] == 'p');
-    if (c->direct) {
-        int rc = direct_workspace_init(c->ws + c->L.dir_i, c->L.dir_i_bytes, (int64_t)B * C, n_items, c->side);
-        if (rc == 0) rc = direct_workspace_init(c->ws + c->L.dir_u, c->L.dir_u_bytes, B, n_users, c->side);
-        if (rc != 0) {
-            delete c;
-            return rc;
+    c->mode = (mode && mode[0] == 'i') ? 1 : ((mode && mode[0] == 'l') ? 2 : 0);
+    if (c->L.dir_i_bytes == 0) c->mode = 2;
+    if (c->mode != 2) {
+        for (int sl = 0; sl < 2; ++sl) {
+            int rc = direct_workspace_init(c->ws + c->L.dir_i[sl], c->L.dir_i_bytes, (int64_t)B * C, n_items, c->side);
+            if (rc == 0) rc = direct_workspace_init(c->ws + c->L.dir_u[sl], c->L.dir_u_bytes, B, n_users, c->side);
+            if (rc != 0) {
+                delete c;
+                return rc;
+            }
         }
     }
     e = cudaStreamSynchronize(c->side);
@@ -185,6 +193,17 @@ extern "C" int b2r_bprmf_ctx_reset(void* ctx) {
 
 static int build_plans(StepCtx* c, int slot, const int64_t* uid, const int64_t* iid, int32_t* err_flag) {
     char* base = c->ws;
+    if (c->mode == 0) {
+        const int64_t nn = (int64_t)c->B * c->C;
+        profile_begin(B2R_PROF_PLAN_I, c->side);
+        int rc = direct_scatter_pair(iid, nn, c->n_items, base + c->L.dir_i[slot], uid, c->B, c->n_users,
+                                     base + c->L.dir_u[slot], err_flag, c->side);
+        if (rc == 0) rc = direct_sort_pair(base + c->L.dir_i[slot], nn, c->n_items, base + c->L.dir_u[slot], c->B, c->n_users, c->side);
+        if (rc != 0) return rc;
+        profile_end(B2R_PROF_PLAN_I, c->side);
+        B2R_CUDA_OK(cudaEventRecord(c->join[slot], c->side));
+        return 0;
+    }
     const PlanBuf& p = c->L.plan[slot];
     const int64_t n = (int64_t)c->B * c->C;
     profile_begin(B2R_PROF_PLAN_I, c->side);
@@ -214,24 +233,24 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
     const int64_t n = (int64_t)B * C;
     int rc;
 
-    if (c->direct) {
+    if (c->mode == 1) {
         // forward (+ plan pairs) -> per-bucket sort of both plans -> update of both tables: three launches, one stream
         float* q = reinterpret_cast<float*>(base + c->L.q);
-        const DirectPlanDev pi = direct_plan_dev(base + c->L.dir_i, n, c->n_items);
-        const DirectPlanDev pu = direct_plan_dev(base + c->L.dir_u, B, c->n_users);
+        const DirectPlanDev pi = direct_plan_dev(base + c->L.dir_i[0], n, c->n_items);
+        const DirectPlanDev pu = direct_plan_dev(base + c->L.dir_u[0], B, c->n_users);
         profile_begin(B2R_PROF_SCORE_FWD, main_s);
         rc = b2r_bprmf_flash_launch(t->U, uid, t->n_users, t->I, iid, t->n_items, nullptr, g, rows, dQ, q, B, C, d, err_flag,
                                     loss_out, reinterpret_cast<unsigned int*>(base + c->L.counter), &pi, &pu, main_s);
         if (rc == 0) {
             profile_end(B2R_PROF_SCORE_FWD, main_s);
             profile_begin(B2R_PROF_PLAN_I, main_s);
-            rc = direct_sort_pair(base + c->L.dir_i, n, c->n_items, base + c->L.dir_u, B, c->n_users, main_s);
+            rc = direct_sort_pair(base + c->L.dir_i[0], n, c->n_items, base + c->L.dir_u[0], B, c->n_users, main_s);
             if (rc != 0) return rc;
             profile_end(B2R_PROF_PLAN_I, main_s);
             const b2r_grad_source su{dQ, nullptr, nullptr, B, 1, 0};
             const b2r_grad_source si{q, g, nullptr, n, C, 0};
-            const b2r_apply_job ji{base + c->L.dir_i, n, t->n_items, &si, nullptr, nullptr, t->I, t->Im, t->Iv};
-            const b2r_apply_job ju{base + c->L.dir_u, B, t->n_users, &su, nullptr, nullptr, t->U, t->Um, t->Uv};
+            const b2r_apply_job ji{base + c->L.dir_i[0], n, t->n_items, &si, nullptr, nullptr, t->I, t->Im, t->Iv};
+            const b2r_apply_job ju{base + c->L.dir_u[0], B, t->n_users, &su, nullptr, nullptr, t->U, t->Um, t->Uv};
             profile_begin(B2R_PROF_SEGMENT_I, main_s);
             rc = direct_apply_pair(&ji, &ju, d, 2, opt, main_s);
             if (rc != 0) return rc;
@@ -239,7 +258,7 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
             return 0;
         }
         if (rc != B2R_E_UNSUPPORTED) return rc;
-        c->direct = false;                                  // shape outside the streaming kernel's class: prefetch form
+        c->mode = 2;                                        // shape outside the streaming kernel's class: legacy form
     }
 
     // everything the side stream does from here on is ordered after what main has enqueued so far
@@ -252,12 +271,8 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
         rc = build_plans(c, cur, uid, iid, err_flag);     // nothing prefetched for this batch: build it now
         if (rc != 0) return rc;
     }
-    // next-round A/B knob (unset = the measured order): B2R_PLAN_AFTER=1 starts the next batch's plan only when this
-    // step's forward kernel has finished, so that the plan's latency/atomic-bound kernels share the SMs with the
-    // HBM-bound update kernel instead of with the issue-bound forward kernel
-    static const bool plan_after = [] { const char* e = getenv("B2R_PLAN_AFTER"); return e && atoi(e) != 0; }();
     const bool prefetch = next_uid != nullptr && next_iid != nullptr;
-    if (prefetch && !plan_after) {
+    if (prefetch) {
         rc = build_plans(c, cur ^ 1, next_uid, next_iid, err_flag);
         if (rc != 0) return rc;
     }
@@ -290,22 +305,17 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
         profile_end(B2R_PROF_SCORE_BWDQ, main_s);
     }
 
-    if (prefetch && plan_after) {
-        B2R_CUDA_OK(cudaEventRecord(c->fork, main_s));                 // after the forward kernel(s)
-        B2R_CUDA_OK(cudaStreamWaitEvent(c->side, c->fork, 0));
-        rc = build_plans(c, cur ^ 1, next_uid, next_iid, err_flag);
-        if (rc != 0) return rc;
-    }
     // join plan(t); then the fused backward+optimizer on both tables in one launch: dI = g * q reads the saved user
     // rows, so the two updates are independent and the small user-table job runs underneath the item-table job
     B2R_CUDA_OK(cudaStreamWaitEvent(main_s, c->join[cur], 0));
     const PlanBuf& p = c->L.plan[cur];
+    const bool dplan = c->mode == 0;
     const b2r_grad_source su{dQ, nullptr, nullptr, B, 1, 0};
     const b2r_grad_source si{q, g, nullptr, n, C, 0};
-    const b2r_apply_job ji{base + p.iws, n, t->n_items, &si, nullptr, nullptr, t->I, t->Im, t->Iv};
-    const b2r_apply_job ju{base + p.uws, B, t->n_users, &su, nullptr, nullptr, t->U, t->Um, t->Uv};
+    const b2r_apply_job ji{base + (dplan ? c->L.dir_i[cur] : p.iws), n, t->n_items, &si, nullptr, nullptr, t->I, t->Im, t->Iv};
+    const b2r_apply_job ju{base + (dplan ? c->L.dir_u[cur] : p.uws), B, t->n_users, &su, nullptr, nullptr, t->U, t->Um, t->Uv};
     profile_begin(B2R_PROF_SEGMENT_I, main_s);
-    rc = b2r_bucket_apply_pair(&ji, &ju, d, 2, opt, main_s);
+    rc = dplan ? direct_apply_pair(&ji, &ju, d, 2, opt, main_s) : b2r_bucket_apply_pair(&ji, &ju, d, 2, opt, main_s);
     if (rc != 0) return rc;
     profile_end(B2R_PROF_SEGMENT_I, main_s);
     return 0;

@@ -504,6 +504,25 @@ __device__ __forceinline__ void direct_sort_job(const DirectSortJob& J, int bid,
     }
 }
 
+// the pairs of one or two id arrays into their direct plans (one launch; CTAs [0, grid_a) work on a)
+__global__ void __launch_bounds__(kBT)
+k_direct_scatter_pair(const int64_t* __restrict__ ids_a, int64_t n_a, int64_t rows_a, const __grid_constant__ DirectPlanDev pa,
+                      int grid_a, const int64_t* __restrict__ ids_b, int64_t n_b, int64_t rows_b,
+                      const __grid_constant__ DirectPlanDev pb, int32_t* err_flag) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {           // counters the following sort accumulates into
+        pa.counters[1] = pa.counters[2] = pa.counters[3] = 0;
+        if (n_b > 0) pb.counters[1] = pb.counters[2] = pb.counters[3] = 0;
+    }
+    if ((int)blockIdx.x < grid_a) {
+        for (int64_t i = (int64_t)blockIdx.x * kBT + threadIdx.x; i < n_a; i += (int64_t)grid_a * kBT)
+            direct_scatter(pa, (uint32_t)checked_id(ids_a[i], rows_a, err_flag), (uint32_t)i);
+    } else {
+        const int gb = (int)gridDim.x - grid_a;
+        for (int64_t i = (int64_t)((int)blockIdx.x - grid_a) * kBT + threadIdx.x; i < n_b; i += (int64_t)gb * kBT)
+            direct_scatter(pb, (uint32_t)checked_id(ids_b[i], rows_b, err_flag), (uint32_t)i);
+    }
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kBT)
 k_bucket_sort_direct(const __grid_constant__ DirectSortJob a, const __grid_constant__ DirectSortJob b) {
@@ -938,6 +957,28 @@ static DirectSortJob direct_sort_job_of(void* ws, int64_t n, int64_t n_rows, int
     J.long_cap = L.long_cap;
     J.heads = reinterpret_cast<uint4*>(base + L.heads);
     return J;
+}
+
+int direct_scatter_pair(const int64_t* ids_a, int64_t n_a, int64_t rows_a, void* ws_a, const int64_t* ids_b, int64_t n_b,
+                        int64_t rows_b, void* ws_b, int32_t* err_flag, cudaStream_t s) {
+    B2R_REQUIRE(ids_a && ws_a && direct_ok(n_a, rows_a), B2R_E_BADARG, "direct_scatter_pair: bad plan a");
+    const DirectPlanDev pa = direct_plan_dev(ws_a, n_a, rows_a);
+    DirectPlanDev pb = pa;
+    int64_t nb = 0;
+    if (ids_b != nullptr && ws_b != nullptr) {
+        B2R_REQUIRE(direct_ok(n_b, rows_b), B2R_E_BADARG, "direct_scatter_pair: bad plan b");
+        pb = direct_plan_dev(ws_b, n_b, rows_b);
+        nb = n_b;
+    }
+    const int cap = sm_count() * 8;
+    int ga = (int)((n_a + kBT * 4 - 1) / (kBT * 4));
+    if (ga > cap) ga = cap;
+    if (ga < 1) ga = 1;
+    int gb = nb > 0 ? (int)((nb + kBT * 4 - 1) / (kBT * 4)) : 0;
+    if (gb > cap) gb = cap;
+    k_direct_scatter_pair<<<ga + gb, kBT, 0, s>>>(ids_a, n_a, rows_a, pa, ga, ids_b, nb, rows_b, pb, err_flag);
+    B2R_LAUNCH_OK("k_direct_scatter_pair");
+    return 0;
 }
 
 int direct_sort_pair(void* ws_a, int64_t n_a, int64_t rows_a, void* ws_b, int64_t n_b, int64_t rows_b, cudaStream_t s) {

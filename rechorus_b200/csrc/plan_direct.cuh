@@ -34,6 +34,10 @@ __device__ __forceinline__ void direct_scatter(const DirectPlanDev& P, uint32_t 
 size_t direct_workspace_bytes(int64_t n, int64_t n_rows);
 int direct_workspace_init(void* ws, size_t ws_bytes, int64_t n, int64_t n_rows, cudaStream_t s);
 DirectPlanDev direct_plan_dev(void* ws, int64_t n, int64_t n_rows);
+// standalone producer (the prefetch form of a step context: the NEXT batch's ids on a side stream): drop the pairs of one or
+// two id arrays into their plans in ONE launch
+int direct_scatter_pair(const int64_t* ids_a, int64_t n_a, int64_t rows_a, void* ws_a, const int64_t* ids_b, int64_t n_b,
+                        int64_t rows_b, void* ws_b, int32_t* err_flag, cudaStream_t s);
 // sort every bucket of one or two plans (b may be NULL) in ONE launch and list their row heads
 int direct_sort_pair(void* ws_a, int64_t n_a, int64_t rows_a, void* ws_b, int64_t n_b, int64_t rows_b, cudaStream_t s);
 // b2r_bucket_apply_pair on plans built this way (job.ws = a direct workspace)

@@ -27,6 +27,14 @@ The global objective is the mean BPR loss over the W*B samples of the step (each
 
 All arithmetic goes through a *backend*: ``CudaBackend`` (the sm_100a kernels; the product) -- the tests inject a
 CPU stand-in to exercise the exchange bookkeeping under gloo.
+
+Two forms of the exchange:
+  * ``exchange="p2p"`` (default on CUDA): every hop above is done BY THE KERNELS over peer-mapped symmetric memory
+    (csrc/shard_p2p.cu, csrc/pairdot_p2p.cu): the routing kernel stores each pair straight into its owner's receive
+    arrays, owners store user vectors into every rank's block and scores into the requester's buffer, g and the dQ rows
+    travel the same way, and the dQ partials are summed from peer memory in rank order.  Six signal-pad barriers order
+    the phases; there is no NCCL call and no tensor glue on the data path.
+  * ``exchange="nccl"``: the collective form described above (the baseline; also what the gloo tests exercise).
 """
 from __future__ import annotations
 
@@ -115,6 +123,10 @@ class ShardedBPRMF:
         self.eps = {"SGD": 0.0, "Adam": 1e-8, "Adagrad": 1e-10}[optimizer] if eps is None else eps
         self.cap_factor = cap_factor
         self.t = 0
+        want = os.environ.get("B2R_SHARD_EXCHANGE", "p2p")
+        is_cuda = torch.device(device).type == "cuda"
+        self.exchange = "p2p" if (is_cuda and backend is None and want != "nccl") else "nccl"
+        self._p2p = None
         g = torch.Generator(device=device).manual_seed(seed * 1000 + self.rank)
         # models/BaseModel.py:29-35 init, one shard per rank
         self.U = torch.empty(self.rows_u, d, device=device).normal_(0.0, init_std, generator=g)
@@ -176,10 +188,11 @@ class ShardedBPRMF:
     def exchange_description(self) -> str:
         if self.world == 1:
             return "none (single rank)"
-        p2p = os.environ.get("B2R_SHARD_P2P") == "1"
-        return ("score routing; scores returned by peer stores from inside the owners' scoring kernel (symmetric memory), "
-                "other hops NCCL all-to-all / all-gather / reduce-scatter" if p2p else
-                "score routing over NCCL: all-to-all x6, all-gather, reduce-scatter per step")
+        if self.exchange == "p2p":
+            return ("score routing, fused into the kernels: pairs / user vectors / scores / g / dQ rows stored into the peers' "
+                    "symmetric-memory buffers by the producing kernels, dQ partials summed from peer memory in rank order; "
+                    "6 signal-pad barriers per step, no NCCL collective on the data path")
+        return "score routing over NCCL: all-to-all x6, all-gather, reduce-scatter per step"
 
     def nvlink_bytes_per_step(self, B: int, C: int) -> int:
         """bytes this rank sends to peers per step (the (W-1)/W remote share of every hop)"""
@@ -253,6 +266,8 @@ class ShardedBPRMF:
         return pred.view(B, C), state
 
     def train_step(self, uid: torch.Tensor, iid: torch.Tensor) -> torch.Tensor:
+        if self.exchange == "p2p":
+            return self._train_step_p2p(uid, iid)
         W, d, be = self.world, self.d, self.backend
         pred, st = self.scores(uid, iid)
         B, C, cap = st["B"], st["C"], st["cap"]
@@ -282,4 +297,139 @@ class ShardedBPRMF:
         ar = torch.arange(W * B, device=dev)
         be.optimizer_rows(self.U, self.state_u, recv_uid, dq_recv, torch.ones(W * B, dtype=torch.float32, device=dev),
                           ar, opt_i)
+        return loss
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # exchange="p2p": the same step with every hop done by kernels over peer-mapped symmetric memory
+    # ---------------------------------------------------------------------------------------------------------------
+    def _p2p_setup(self, B: int, C: int):
+        import ctypes as Ct
+        from . import lib as _lib
+        W, d, dev = self.world, self.d, self.U.device
+        n = B * C
+        cap = self.capacity(n)
+        L = _lib.load()
+        lay, off = {}, 0
+
+        def take(name, nbytes):
+            nonlocal off
+            lay[name] = off
+            off += (nbytes + 255) // 256 * 256
+
+        take("rows_in", W * cap * 8)
+        take("qidx_in", W * cap * 8)
+        take("scores_in", W * cap * 4)
+        take("g_in", W * cap * 4)
+        for par in (0, 1):                      # written by the NEXT step's routing while this step's user update reads
+            take(f"ureq_rows{par}", W * B * 8)
+            take(f"ureq_q{par}", W * B * 8)
+        take("q_all", W * B * d * 4)
+        take("dqp", W * B * d * 4)
+        take("dqu_in", W * B * d * 4)
+        total = off
+        if W > 1:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(total, dtype=torch.uint8, device=dev)
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            bases = [int(hdl.buffer_ptrs[r]) for r in range(W)]
+        else:
+            buf, hdl = torch.empty(total, dtype=torch.uint8, device=dev), None
+            bases = [buf.data_ptr()]
+        buf.zero_()
+
+        def view(name, dtype, shape):
+            nb = torch.empty((), dtype=dtype).element_size()
+            cnt = 1
+            for x in shape:
+                cnt *= x
+            return buf[lay[name]:lay[name] + cnt * nb].view(dtype).view(*shape)
+
+        def table(name, region_bytes=0):
+            """host array of W device pointers: rank r's buffer `name` (+ this rank's region inside it)"""
+            return (Ct.c_void_p * W)(*[bases[r] + lay[name] + self.rank * region_bytes for r in range(W)])
+
+        x = types_ns = type("P2P", (), {})()
+        x.B, x.C, x.n, x.cap, x.hdl, x.buf = B, C, n, cap, hdl, buf
+        x.rows_in, x.qidx_in = view("rows_in", torch.int64, (W * cap,)), view("qidx_in", torch.int64, (W * cap,))
+        x.scores_in, x.g_in = view("scores_in", torch.float32, (W * cap,)), view("g_in", torch.float32, (W * cap,))
+        x.ureq_rows = [view(f"ureq_rows{p}", torch.int64, (W * B,)) for p in (0, 1)]
+        x.ureq_q = [view(f"ureq_q{p}", torch.int64, (W * B,)) for p in (0, 1)]
+        x.q_all, x.dqp = view("q_all", torch.float32, (W * B, d)), view("dqp", torch.float32, (W * B, d))
+        x.dqu_in = view("dqu_in", torch.float32, (W * B, d))
+        # where this rank writes at each peer
+        x.t_rows, x.t_qidx = table("rows_in", cap * 8), table("qidx_in", cap * 8)
+        x.t_g = table("g_in", cap * 4)
+        x.t_ureq_rows = [table(f"ureq_rows{p}", B * 8) for p in (0, 1)]
+        x.t_ureq_q = [table(f"ureq_q{p}", B * 8) for p in (0, 1)]
+        x.t_q_all, x.t_dqp = table("q_all"), table("dqp")
+        x.t_dqu = table("dqu_in", B * d * 4)
+        x.score_tab = torch.tensor([bases[r] + lay["scores_in"] + self.rank * cap * 4 for r in range(W)], dtype=torch.int64,
+                                   device=dev)
+        # local scratch
+        x.slot_of = torch.empty(n, dtype=torch.int32, device=dev)
+        x.slot_of_u = torch.empty(B, dtype=torch.int32, device=dev)
+        x.tot = torch.zeros(2 * W, dtype=torch.int32, device=dev)
+        x.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        x.route_ws = torch.empty(L.b2r_route_workspace_bytes(B, W), dtype=torch.uint8, device=dev)
+        x.dq = torch.empty((B, d), dtype=torch.float32, device=dev)
+        x.ones = torch.ones(W * B, dtype=torch.float32, device=dev)
+        x.arange = torch.arange(W * B, dtype=torch.int64, device=dev)
+        x.step = 0
+        if hdl is not None:
+            hdl.barrier(channel=0)              # every rank's buffers are zeroed before anyone writes into them
+        return x
+
+    def _barrier(self, x, ch: int):
+        if x.hdl is not None:
+            x.hdl.barrier(channel=ch)
+
+    def _train_step_p2p(self, uid: torch.Tensor, iid: torch.Tensor) -> torch.Tensor:
+        from . import lib as _lib, ops
+        W, d, be, me = self.world, self.d, self.backend, self.rank
+        B, C = iid.shape
+        x = self._p2p
+        if x is None or x.B != B or x.C != C:
+            x = self._p2p = self._p2p_setup(B, C)
+        L = _lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        ef = ops.err_flag(uid.device).data_ptr()
+        uid, iid = uid.contiguous(), iid.contiguous()
+        par = x.step & 1
+        x.step += 1
+        # 0. route: pairs and user-row requests land in their owners' receive arrays (peer stores from the kernel)
+        _lib.check(L.b2r_route_ids(iid.data_ptr(), B, C, W, self.rows_i, self.n_items, x.t_rows, x.t_qidx, me * B, x.cap,
+                                   x.slot_of.data_ptr(), x.tot.data_ptr(), x.overflow.data_ptr(), x.route_ws.data_ptr(),
+                                   x.route_ws.numel(), ef, st), "b2r_route_ids(items)")
+        _lib.check(L.b2r_route_ids(uid.data_ptr(), B, 1, W, self.rows_u, self.n_users, x.t_ureq_rows[par], x.t_ureq_q[par],
+                                   me * B, B, x.slot_of_u.data_ptr(), x.tot.data_ptr() + 4 * W, x.overflow.data_ptr(),
+                                   x.route_ws.data_ptr(), x.route_ws.numel(), ef, st), "b2r_route_ids(users)")
+        torch._assert_async(x.overflow[0] == 0)               # ids too skewed for cap_factor
+        self._barrier(x, 0)
+        # 1. owners of user rows fill every rank's block of user vectors (gather + all-gather in one kernel)
+        _lib.check(L.b2r_serve_rows(self.U.data_ptr(), self.U.shape[0], x.ureq_rows[par].data_ptr(), x.ureq_q[par].data_ptr(),
+                                    W * B, x.t_q_all, W, d, ef, st), "b2r_serve_rows")
+        self._barrier(x, 1)
+        # 2. owners score their pairs; each score is stored into the requester's buffer by the scoring kernel
+        be.pairdot_p2p(x.q_all, x.qidx_in, self.I, x.rows_in, x.score_tab, x.cap)
+        self._barrier(x, 2)
+        # 3. home: scores -> [B, C], BPR loss + gradient (objective = mean over the W*B samples), g -> owners
+        pred = x.scores_in[x.slot_of.long()].view(B, C)
+        loss, g = be.bpr_loss_and_grad(pred)
+        _lib.check(L.b2r_scatter_f32_to_peers(g.data_ptr(), x.slot_of.data_ptr(), x.n, x.t_g, W, x.cap, 1.0 / W, st),
+                   "b2r_scatter_f32_to_peers")
+        self._barrier(x, 3)
+        # 4. owners: dQ partials per (source, sample), then the fused row-sparse optimizer on the item shard
+        self.t += 1
+        opt = be.make_opt(self.opt_name, self.lr, self.betas, self.eps, self.l2, self.t)
+        x.dqp.zero_()
+        be.sum_runs(x.dqp, x.qidx_in, x.rows_in, x.g_in, self.I)
+        be.optimizer_rows(self.I, self.state_i, x.rows_in, x.q_all, x.g_in, x.qidx_in, opt)
+        self._barrier(x, 4)
+        # 5. home: dQ = sum of the owners' partials read from peer memory in rank order; rows -> user-row owners
+        _lib.check(L.b2r_sum_rows_from_peers(x.t_dqp, W, me * B * d, x.dq.data_ptr(), B * d, st), "b2r_sum_rows_from_peers")
+        _lib.check(L.b2r_scatter_rows_to_peers(x.dq.data_ptr(), x.slot_of_u.data_ptr(), B, x.t_dqu, W, B, d, st),
+                   "b2r_scatter_rows_to_peers")
+        self._barrier(x, 5)
+        # 6. owners: fused row-sparse optimizer on the user shard
+        be.optimizer_rows(self.U, self.state_u, x.ureq_rows[par], x.dqu_in, x.ones, x.arange, opt)
         return loss

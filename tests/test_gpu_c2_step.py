@@ -180,7 +180,7 @@ def test_contract_route_equals_train_step_at_full_size():
         assert (pa - pb).abs().max() <= 1e-6, k
 
 
-@pytest.mark.parametrize("kind", ["one_row", "two_hot_buckets"])
+@pytest.mark.parametrize("kind", ["one_row", "two_hot_buckets"])  # "one_row": really two (see below)
 def test_train_step_degenerate_id_distributions_match_oracle(kind):
     """skew the fixed-capacity bucket regions of the step's index plan cannot hold: every pair on ONE row (one bucket
     receives the whole batch through the spill list and is merge-sorted in chunks) / two hot buckets plus uniform rest"""
@@ -190,7 +190,8 @@ def test_train_step_degenerate_id_distributions_match_oracle(kind):
     uid = torch.randint(1, N_USERS, (Bs,), generator=g)
     iid = torch.randint(1, N_ITEMS, (Bs, C), generator=g)
     if kind == "one_row":
-        iid[:] = 7
+        iid[:, 0] = 9                      # two rows carry the whole batch: 1,024 positives on row 9, 101,376 negatives on
+        iid[:, 1:] = 7                     # row 7 -- one bucket receives everything (spill list, chunked merge sort)
         uid[:] = 3
     else:
         iid[:, ::3] = torch.randint(1000, 1400, (Bs, (C + 2) // 3), generator=g)          # ~34k pairs in one 512-row bucket
@@ -212,6 +213,7 @@ def test_train_step_degenerate_id_distributions_match_oracle(kind):
         for name, (w0, m0, v0), gr, W, idx in (("U", before[0:3], gU, U, uud), ("I", before[3:6], gI, I, uid_d)):
             w1, _, _ = _lazy_adam(w0, m0, v0, gr, t)
             ok = gr.abs() > 1e-6
+            assert bool(ok.any())
             assert ((W[idx].cpu().double() - w1).abs()[ok]).max() <= 2e-6, (kind, name, t)
     ops.check_ids()
     m2 = _model()                                             # and the same bits on a second run

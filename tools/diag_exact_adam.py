@@ -29,6 +29,13 @@ for step in range(25):
     loss.backward()
     model.optimizer.step()
     ref.step({"user_id": uid, "item_id": iid}, shuffle=False)
+    if os.environ.get("DIAG_FLUSH"):
+        model.optimizer.flush()                     # exact mode must be invariant to extra flushes
+        e_i = (model.i_embeddings.weight.detach().cpu() - ref.p["i_embeddings.weight"].detach()).abs().max(dim=1).values
+        bad = (e_i > 1e-5).nonzero().reshape(-1).tolist()
+        if bad:
+            print("step", step + 1, "rows off", [(r, float(e_i[r]), sorted(set(hist_i.get(r, [])))[-4:]) for r in bad[:5]],
+                  "ids this step", sorted(set(iid.reshape(-1).tolist()))[:0])
     for r in iid.reshape(-1).tolist():
         hist_i.setdefault(r, []).append(step + 1)
     gi = ref.p["i_embeddings.weight"].grad
