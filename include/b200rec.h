@@ -388,6 +388,18 @@ B2R_API int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const int
                          float* loss_out, int32_t* err_flag, b2r_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * List-wise ranking losses of the impression models: value and closed-form gradient of ImpressionModel.loss
+ * (models/BaseImpressionModel.py:44-128).  pred [B, Cn] float32, target [B, Cn] int64 (1 clicked, 0 shown, -1 padding);
+ * columns < max_pos are the positive slots (:55-58; the reference also reads column max_pos: max_pos < Cn).
+ * kind: 0 'BPR' (reweight between sigmoid and log, :82-85), 1 'BPR..after' (:73-75), 2 'BPR..before' (:76-78), each
+ * with hard = 0/1 ('hard' in the name, :63-68); 3 'listnet' (:88-97), 4 'softmaxCE' (:99-110), 5 'attention_rank'
+ * (:112-128).  loss_out: 1 float; grad_pred [B, Cn] = d loss / d pred (may be NULL).  ws: b2r_listwise_workspace_bytes(B).
+ * ---------------------------------------------------------------------------------------------- */
+B2R_API size_t b2r_listwise_workspace_bytes(int B);
+B2R_API int b2r_listwise_loss(const float* pred, const int64_t* target, int B, int Cn, int max_pos, int kind, int hard,
+                              float* loss_out, float* grad_pred, void* ws, size_t ws_bytes, b2r_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Row-sharded tables (BASELINE config 5): the exchange done by kernels over peer-mapped memory (symmetric-memory
  * buffers of the ranks of one box; NVLink loads / stores) instead of collectives between kernels.  No reference
  * counterpart (the reference is single-device); contract: SURVEY.md 8(e).  Pointer tables are HOST arrays of W device

@@ -296,6 +296,57 @@ def loss_and_grads(model: str, p: Params, batch: Dict[str, Tensor], num_heads: i
     return pred.detach(), loss.detach(), grads
 
 
+# --------------------------------------------------------------------------------------------------
+# list-wise losses of the impression models (models/BaseImpressionModel.py:44-128)
+# --------------------------------------------------------------------------------------------------
+
+def listwise_loss(pred: Tensor, target: Tensor, loss_n: str, max_pos: int) -> Tensor:
+    """ImpressionModel.loss restated row by row (BaseImpressionModel.py:44-128).  pred [B, Cn], target [B, Cn] in
+    {1, 0, -1 (padding)}; columns < max_pos are the positive slots (:55-58).  Supported names: every 'BPR*' form except
+    'simple' (which returns a vector in the reference, :79-81), 'listnet', 'softmaxCE', 'attention_rank'.  The batch-wide
+    maxima the reference subtracts before its softmaxes (:62,65,68,90,91,114,117) cancel and are replaced by row maxima."""
+    B, Cn = pred.shape
+    valid = target != -1
+    col = torch.arange(Cn).unsqueeze(0).expand(B, Cn)
+    P, N = valid & (col < max_pos), valid & (col >= max_pos)
+    ninf = torch.full_like(pred, float("-inf"))
+
+    def masked_softmax(x, m):
+        return torch.softmax(torch.where(m, x, ninf), dim=1)
+
+    if "BPR" in loss_n:
+        if "simple" in loss_n:
+            raise ValueError("BPR...simple is not back-propagatable in the reference (returns a [B] vector)")
+        nw = masked_softmax(pred, N)                                                  # :60-62
+        pw = masked_softmax(-pred if "hard" in loss_n else pred, P)                   # :63-68
+        diff = pred.unsqueeze(2) - pred.unsqueeze(1)                                  # [B, i, j] = x_i - x_j
+        pair = (P.unsqueeze(2) & N.unsqueeze(1)).to(pred.dtype)
+        w2 = pw.unsqueeze(2) * nw.unsqueeze(1)
+        if "after" in loss_n:                                                         # :73-75
+            return (F.softplus(-diff) * w2 * pair).sum(dim=(1, 2)).mean()
+        if "before" in loss_n:                                                        # :76-78
+            z = (diff * pair * nw.unsqueeze(1)).sum(dim=2) * pw                       # 0 outside P -> softplus(0) = ln 2
+            return F.softplus(-z).sum(dim=1).mean()
+        return (-(torch.sigmoid(diff) * w2 * pair).sum(dim=(1, 2)).log()).mean()      # :82-85
+    have_neg = valid[:, max_pos].to(pred.dtype)                                       # :53
+    scale = have_neg / have_neg.sum() * B                                             # :96,109,126
+    tw = masked_softmax(target.to(pred.dtype), valid)                                 # :89-90,113-114
+    if loss_n == "listnet":                                                           # :88-97: softmax over ALL columns
+        logp = torch.log_softmax(pred, dim=1)
+        return (-(tw * torch.where(valid, logp, torch.zeros_like(logp))).sum(dim=1) * scale).mean()
+    p = masked_softmax(pred, valid)
+    if loss_n == "softmaxCE":                                                         # :99-110
+        pos_len = (target == 1).sum(dim=1).to(pred.dtype)
+        lp = torch.where(P, p, torch.ones_like(p)).log()
+        return (-(lp.sum(dim=1) / pos_len) * scale).mean()
+    if loss_n == "attention_rank":                                                    # :112-128
+        l1 = -(tw * torch.where(valid, p, torch.ones_like(p)).log()).sum(dim=1)
+        p2 = torch.where(valid & (p != 1), p, torch.zeros_like(p))
+        l2 = -((1 - tw) * (1 - p2).log()).sum(dim=1)
+        return ((l1 + l2) * scale).mean()
+    raise ValueError("Undefined loss function: {}".format(loss_n))
+
+
 class ReferenceStyleTrainer:
     """The reference's per-batch training step as helpers/BaseRunner.py:184-207 performs it on CPU:
     candidate shuffle, zero_grad, forward, un-shuffle, loss, backward with DENSE embedding grads, and a

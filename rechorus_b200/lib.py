@@ -124,6 +124,9 @@ SIGNATURES = {
                                          C.c_void_p]),
     "b2r_pairdot_fwd_p2p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "b2r_listwise_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "b2r_listwise_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b2r_route_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "b2r_route_ids": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

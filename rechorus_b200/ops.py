@@ -571,6 +571,50 @@ class _BprLoss(torch.autograd.Function):
         return grad * gl
 
 
+def listwise_kind(loss_n: str) -> Tuple[int, int]:
+    """(kind, hard) of b2r_listwise_loss for a reference --loss_n string (BaseImpressionModel.py:26-27,58-128)"""
+    if "BPR" in loss_n:
+        if "simple" in loss_n:
+            raise ValueError("loss 'BPR...simple' returns a vector in the reference (BaseImpressionModel.py:79-81) and cannot "
+                             "be back-propagated there; not provided")
+        kind = 1 if "after" in loss_n else (2 if "before" in loss_n else 0)
+        return kind, 1 if "hard" in loss_n else 0
+    table = {"listnet": 3, "softmaxCE": 4, "attention_rank": 5}
+    if loss_n not in table:
+        raise ValueError("Undefined loss function: {}".format(loss_n))
+    return table[loss_n], 0
+
+
+class _ListwiseLoss(torch.autograd.Function):
+    """ImpressionModel.loss (BaseImpressionModel.py:44-128): value and closed-form gradient from b2r_listwise_loss."""
+
+    @staticmethod
+    def forward(ctx, pred, target, kind, hard, max_pos):
+        _need_cuda(pred, target)
+        pred, target = _f32c(pred, "prediction"), _i64c(target, "target")
+        if pred.dim() != 2 or tuple(target.shape) != tuple(pred.shape):
+            raise ValueError("prediction and target must both be [B, Cn]")
+        B, Cn = pred.shape
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred)
+        L = _lib.load()
+        ws = _ws(L.b2r_listwise_workspace_bytes(B), pred.device)
+        _lib.check(L.b2r_listwise_loss(_p(pred), _p(target), B, Cn, int(max_pos), int(kind), int(hard), _p(loss), _p(grad),
+                                       _p(ws), ws.numel(), _stream()), "b2r_listwise_loss")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gl):
+        (grad,) = ctx.saved_tensors
+        return grad * gl, None, None, None, None
+
+
+def listwise_loss(pred: torch.Tensor, target: torch.Tensor, loss_n: str, max_pos: int) -> torch.Tensor:
+    kind, hard = listwise_kind(loss_n)
+    return _ListwiseLoss.apply(pred, target, kind, hard, max_pos)
+
+
 def embedding(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     return _Gather.apply(table, ids)
 

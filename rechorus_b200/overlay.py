@@ -124,6 +124,44 @@ def install(ref_src: str = DEFAULT_REF, b200_runner: bool = False):
             self._base_init(args, corpus)
 
     ref_bprmf.BPRMF, ref_neumf.NeuMF, ref_sasrec.SASRec = BPRMF, NeuMF, SASRec
+    # --model_mode Impression (main.py:164: '{0}.{0}{1}'): the reference's own ImpressionModel / ImpressionSeqModel hosts
+    # (flags, reader, runner, Dataset) with the forward on the kernels and the list-wise loss as one kernel family
+    import models.BaseImpressionModel as RI
+
+    class _ImpLoss:
+        def loss(self, out_dict, target=None):
+            from . import ops
+            return ops.listwise_loss(out_dict["prediction"], target, self.loss_n, self.train_max_pos_item)
+
+    class BPRMFImpression(_ImpLoss, plugin.BPRMFKernels, RI.ImpressionModel):
+        reader, runner = "ImpressionReader", "ImpressionRunner"
+        extra_log_args = ["emb_size", "batch_size"]
+
+        @staticmethod
+        def parse_model_args(parser):
+            parser = plugin.BPRMFKernels.parse_model_args(parser)
+            return RI.ImpressionModel.parse_model_args(parser)
+
+        def __init__(self, args, corpus):
+            RI.ImpressionModel.__init__(self, args, corpus)
+            self.__dict__["_b2r_vectors"] = True
+            self._base_init(args, corpus)
+
+    class SASRecImpression(_ImpLoss, plugin.SASRecKernels, RI.ImpressionSeqModel):
+        reader, runner = "ImpressionSeqReader", "ImpressionRunner"
+        extra_log_args = ["emb_size", "num_layers", "num_heads"]
+
+        @staticmethod
+        def parse_model_args(parser):
+            parser = plugin.SASRecKernels.parse_model_args(parser)
+            return RI.ImpressionSeqModel.parse_model_args(parser)
+
+        def __init__(self, args, corpus):
+            RI.ImpressionSeqModel.__init__(self, args, corpus)
+            self.__dict__["_b2r_vectors"] = True
+            self._base_init(args, corpus)
+
+    ref_bprmf.BPRMFImpression, ref_sasrec.SASRecImpression = BPRMFImpression, SASRecImpression
     if b200_runner:
         # main.py:10 `from helpers import *` imports what helpers.__all__ names; add the runner module there and let
         # the model classes choose it (main.py:166: eval('{0}.{0}'.format(model_name.runner)))
@@ -136,7 +174,8 @@ def install(ref_src: str = DEFAULT_REF, b200_runner: bool = False):
             helpers.__all__.append("B200Runner")
         for cls in (BPRMF, NeuMF, SASRec):
             cls.runner = "B200Runner"
-    return {"BPRMF": BPRMF, "NeuMF": NeuMF, "SASRec": SASRec}
+    return {"BPRMF": BPRMF, "NeuMF": NeuMF, "SASRec": SASRec, "BPRMFImpression": BPRMFImpression,
+            "SASRecImpression": SASRecImpression}
 
 
 def main(argv=None):

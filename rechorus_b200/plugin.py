@@ -158,7 +158,13 @@ class BPRMFKernels(_KernelModelMixin):
                 opt.flush()
         u = ops.embedding(self.u_embeddings.weight, u_ids)            # [B, d]   (gather kernel)
         pred = ops.score(u, self.i_embeddings.weight, i_ids)          # [B, C]   (gather + dot kernel)
-        return {"prediction": pred.view(feed_dict["batch_size"], -1)}
+        out = {"prediction": pred.view(feed_dict["batch_size"], -1)}
+        if getattr(self, "_b2r_vectors", False):
+            # BPRMFBase.forward also returns the vectors (BPRMF.py:43-45) -- re-rankers stack them under a base ranker
+            # (BaseRerankerModel.py:82-83).  The plain BPRMF drops them (:60-62), the Impression variant keeps them.
+            out["u_v"] = u.unsqueeze(1).expand(-1, i_ids.shape[1], -1)
+            out["i_v"] = ops.embedding(self.i_embeddings.weight, i_ids)
+        return out
 
     def query_rows(self, feed_dict):
         with torch.no_grad():
@@ -349,7 +355,40 @@ class SASRecKernels(_KernelModelMixin):
         lengths = feed_dict["lengths"]          # [B]
         h = self.user_state(history, lengths)
         pred = ops.score(h, self.i_embeddings.weight, i_ids)
-        return {"prediction": pred.view(history.shape[0], -1)}
+        out = {"prediction": pred.view(history.shape[0], -1)}
+        if getattr(self, "_b2r_vectors", False):                       # SASRec.py:83-86, kept by SASRecImpression (:121-122)
+            out["u_v"] = h.unsqueeze(1).expand(-1, i_ids.shape[1], -1)
+            out["i_v"] = ops.embedding(self.i_embeddings.weight, i_ids)
+        return out
+
+
+class ImpressionLossMixin:
+    """models/BaseImpressionModel.py:10-128 (ImpressionModel): the list-wise losses over multiple positives / negatives per
+    impression, as one kernel family (ops.listwise_loss).  Flags and attribute names are the reference's; the reader and
+    runner of the impression setting (ImpressionReader / ImpressionRunner) are the reference's own under the overlay."""
+
+    @staticmethod
+    def parse_impression_args(parser):
+        parser.add_argument("--loss_n", type=str, default="BPR",
+                            help="BPR[hard][after|before] | listnet | softmaxCE | attention_rank (BaseImpressionModel.py:26)")
+        parser.add_argument("--train_max_pos_item", type=int, default=20, help="max positive item sample for training")
+        parser.add_argument("--train_max_neg_item", type=int, default=20, help="max negative item sample for training")
+        parser.add_argument("--test_max_pos_item", type=int, default=20, help="max positive item sample for evaluation")
+        parser.add_argument("--test_max_neg_item", type=int, default=20, help="max negative item sample for evaluation")
+        return parser
+
+    def _impression_init(self, args):
+        self.loss_n = args.loss_n
+        self.train_max_pos_item, self.train_max_neg_item = args.train_max_pos_item, args.train_max_neg_item
+        self.test_max_pos_item, self.test_max_neg_item = args.test_max_pos_item, args.test_max_neg_item
+        ops.listwise_kind(self.loss_n)                    # unknown names fail at construction, not at the first batch
+        self.__dict__["_b2r_vectors"] = True
+
+    # BaseImpressionModel.py:44: loss(out_dict, target) -- the ImpressionRunner passes the batch's labels
+    def loss(self, out_dict: dict, target=None) -> torch.Tensor:
+        if target is None:
+            raise ValueError("impression losses need the label tensor (ImpressionRunner passes it as `target`)")
+        return ops.listwise_loss(out_dict["prediction"], target, self.loss_n, self.train_max_pos_item)
 
 
 # ======================================================================================================
@@ -593,4 +632,38 @@ class SASRec(SASRecKernels, SequentialModel):
 
     def __init__(self, args, corpus):
         SequentialModel.__init__(self, args, corpus)
+        self._base_init(args, corpus)
+
+
+class BPRMFImpression(ImpressionLossMixin, BPRMFKernels, GeneralModel):
+    """Drop-in for models/general/BPRMF.py:65-80 (stand-alone form: bring your own impression batches)."""
+    reader, runner = "ImpressionReader", "ImpressionRunner"
+    extra_log_args = ["emb_size", "batch_size"]
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser = BPRMFKernels.parse_model_args(parser)
+        parser = ImpressionLossMixin.parse_impression_args(parser)
+        return GeneralModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        GeneralModel.__init__(self, args, corpus)
+        self._impression_init(args)
+        self._base_init(args, corpus)
+
+
+class SASRecImpression(ImpressionLossMixin, SASRecKernels, SequentialModel):
+    """Drop-in for models/sequential/SASRec.py:107-122."""
+    reader, runner = "ImpressionSeqReader", "ImpressionRunner"
+    extra_log_args = ["emb_size", "num_layers", "num_heads"]
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser = SASRecKernels.parse_model_args(parser)
+        parser = ImpressionLossMixin.parse_impression_args(parser)
+        return SequentialModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        SequentialModel.__init__(self, args, corpus)
+        self._impression_init(args)
         self._base_init(args, corpus)
