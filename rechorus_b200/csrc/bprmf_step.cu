@@ -271,8 +271,11 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
         rc = build_plans(c, cur, uid, iid, err_flag);     // nothing prefetched for this batch: build it now
         if (rc != 0) return rc;
     }
+    // B2R_PLAN_AFTER=1 (A/B knob): start the next batch's plan only when this step's forward kernel has finished, so that
+    // the plan's kernels share the SMs with the HBM-bound update kernel instead of with the single-wave forward kernel
+    static const bool plan_after = [] { const char* e = getenv("B2R_PLAN_AFTER"); return e && atoi(e) != 0; }();
     const bool prefetch = next_uid != nullptr && next_iid != nullptr;
-    if (prefetch) {
+    if (prefetch && !plan_after) {
         rc = build_plans(c, cur ^ 1, next_uid, next_iid, err_flag);
         if (rc != 0) return rc;
     }
@@ -305,6 +308,12 @@ extern "C" int b2r_bprmf_train_step(void* ctx, const b2r_bprmf_tables* t, const 
         profile_end(B2R_PROF_SCORE_BWDQ, main_s);
     }
 
+    if (prefetch && plan_after) {
+        B2R_CUDA_OK(cudaEventRecord(c->fork, main_s));                 // after the forward kernel(s)
+        B2R_CUDA_OK(cudaStreamWaitEvent(c->side, c->fork, 0));
+        rc = build_plans(c, cur ^ 1, next_uid, next_iid, err_flag);
+        if (rc != 0) return rc;
+    }
     // join plan(t); then the fused backward+optimizer on both tables in one launch: dI = g * q reads the saved user
     // rows, so the two updates are independent and the small user-table job runs underneath the item-table job
     B2R_CUDA_OK(cudaStreamWaitEvent(main_s, c->join[cur], 0));
