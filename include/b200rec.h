@@ -203,6 +203,18 @@ typedef struct b2r_apply_job {
 B2R_API int b2r_bucket_apply_pair(const b2r_apply_job* a, const b2r_apply_job* b, int d, int mode, const b2r_optim* opt,
                                   b2r_stream_t stream);
 
+/* "Direct" plans: the same plan as b2r_bucket_partition in two launches instead of four -- every (row, position) pair is
+ * dropped into the fixed-capacity region of its row range with one L2 atomic (pairs beyond a region's capacity go to a
+ * spill list), then one kernel sorts every bucket and lists the row heads.  b2r_direct_plan_apply == b2r_bucket_apply on
+ * such a plan.  The workspace must be initialised once with b2r_direct_plan_init; build/apply may then alternate. */
+B2R_API size_t b2r_direct_plan_workspace_bytes(int64_t n, int64_t n_rows);
+B2R_API int b2r_direct_plan_init(void* ws, size_t ws_bytes, int64_t n, int64_t n_rows, b2r_stream_t stream);
+B2R_API int b2r_direct_plan_build(const int64_t* ids, int64_t n, int64_t n_rows, int64_t ignore_id, int64_t ignore_n,
+                                  void* ws, size_t ws_bytes, int32_t* err_flag, b2r_stream_t stream);
+B2R_API int b2r_direct_plan_apply(const void* ws, int64_t n, int64_t n_rows, int d, const b2r_grad_source* s0,
+                                  const b2r_grad_source* s1, int mode, float* dense, float* W, float* m, float* v,
+                                  const b2r_optim* opt, b2r_stream_t stream);
+
 /* Fast, order-nondeterministic alternative to plan+segment for mode 1 (dense += via red.global.add.v4.f32) */
 B2R_API int b2r_scatter_add_atomic(const int64_t* ids, int64_t n_rows, const b2r_grad_source* s, int d,
                            float* dense, int32_t* err_flag, b2r_stream_t stream);

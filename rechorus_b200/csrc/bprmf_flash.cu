@@ -329,9 +329,10 @@ int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, 
     const bool plan = plan_i != nullptr && plan_u != nullptr;
     const DirectPlanDev none{};
     const DirectPlanDev pi = plan ? *plan_i : none, pu = plan ? *plan_u : none;
-    // variant knob for A/B runs: B2R_FLASH="<VPL><RCH><ST>", default 223 (two float4 per lane, 2 rows per group per chunk,
-    // 3 stages); 143 is the first version of this kernel (one float4 per lane, 4 rows per chunk)
-    static const int variant = [] { const char* e = getenv("B2R_FLASH"); return e ? atoi(e) : 223; }();
+    // variant knob for A/B runs: B2R_FLASH="<VPL><RCH><ST>".  Default 143 (one float4 per lane, 4 rows per group per chunk,
+    // 3 stages: 0.1501 ms per config-2 step); 223 / 243 (two float4 per lane) execute fewer instructions but spill under
+    // the 64-register cap the single-wave residency needs and measure 0.152 ms (profiles/README r2).
+    static const int variant = [] { const char* e = getenv("B2R_FLASH"); return e ? atoi(e) : 143; }();
 #define B2R_FL(D_, VPL, RCH, ST, PLAN)                                                                               \
     do {                                                                                                             \
         const int smem = kFlWarps * (ST * RCH * VPL * 32 * 16 + cpad * 8);                                           \
@@ -347,9 +348,9 @@ int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, 
     } while (0)
 #define B2R_FL_V(D_, PLAN)                                                                                           \
     do {                                                                                                             \
-        if (variant == 143) B2R_FL(D_, 1, 4, 3, PLAN);                                                               \
+        if (variant == 223) B2R_FL(D_, 2, 2, 3, PLAN);                                                               \
         else if (variant == 243) B2R_FL(D_, 2, 4, 3, PLAN);                                                          \
-        else B2R_FL(D_, 2, 2, 3, PLAN);                                                                              \
+        else B2R_FL(D_, 1, 4, 3, PLAN);                                                                              \
     } while (0)
 #define B2R_FL_D(D_)                                                                                                 \
     do {                                                                                                             \

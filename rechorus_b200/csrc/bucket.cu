@@ -508,14 +508,17 @@ __device__ __forceinline__ void direct_sort_job(const DirectSortJob& J, int bid,
 __global__ void __launch_bounds__(kBT)
 k_direct_scatter_pair(const int64_t* __restrict__ ids_a, int64_t n_a, int64_t rows_a, const __grid_constant__ DirectPlanDev pa,
                       int grid_a, const int64_t* __restrict__ ids_b, int64_t n_b, int64_t rows_b,
-                      const __grid_constant__ DirectPlanDev pb, int32_t* err_flag) {
+                      const __grid_constant__ DirectPlanDev pb, int32_t* err_flag, int64_t ignore_id, int64_t ignore_n) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {           // counters the following sort accumulates into
         pa.counters[1] = pa.counters[2] = pa.counters[3] = 0;
         if (n_b > 0) pb.counters[1] = pb.counters[2] = pb.counters[3] = 0;
     }
     if ((int)blockIdx.x < grid_a) {
-        for (int64_t i = (int64_t)blockIdx.x * kBT + threadIdx.x; i < n_a; i += (int64_t)grid_a * kBT)
-            direct_scatter(pa, (uint32_t)checked_id(ids_a[i], rows_a, err_flag), (uint32_t)i);
+        for (int64_t i = (int64_t)blockIdx.x * kBT + threadIdx.x; i < n_a; i += (int64_t)grid_a * kBT) {
+            const int64_t id = ids_a[i];
+            if (i < ignore_n && id == ignore_id) continue;            // padding positions contribute nothing (plan a only)
+            direct_scatter(pa, (uint32_t)checked_id(id, rows_a, err_flag), (uint32_t)i);
+        }
     } else {
         const int gb = (int)gridDim.x - grid_a;
         for (int64_t i = (int64_t)((int)blockIdx.x - grid_a) * kBT + threadIdx.x; i < n_b; i += (int64_t)gb * kBT)
@@ -959,8 +962,18 @@ static DirectSortJob direct_sort_job_of(void* ws, int64_t n, int64_t n_rows, int
     return J;
 }
 
+static int direct_scatter_pair_ex(const int64_t* ids_a, int64_t n_a, int64_t rows_a, void* ws_a, const int64_t* ids_b,
+                                  int64_t n_b, int64_t rows_b, void* ws_b, int32_t* err_flag, int64_t ignore_id,
+                                  int64_t ignore_n, cudaStream_t s);
+
 int direct_scatter_pair(const int64_t* ids_a, int64_t n_a, int64_t rows_a, void* ws_a, const int64_t* ids_b, int64_t n_b,
                         int64_t rows_b, void* ws_b, int32_t* err_flag, cudaStream_t s) {
+    return direct_scatter_pair_ex(ids_a, n_a, rows_a, ws_a, ids_b, n_b, rows_b, ws_b, err_flag, -1, 0, s);
+}
+
+static int direct_scatter_pair_ex(const int64_t* ids_a, int64_t n_a, int64_t rows_a, void* ws_a, const int64_t* ids_b,
+                                  int64_t n_b, int64_t rows_b, void* ws_b, int32_t* err_flag, int64_t ignore_id,
+                                  int64_t ignore_n, cudaStream_t s) {
     B2R_REQUIRE(ids_a && ws_a && direct_ok(n_a, rows_a), B2R_E_BADARG, "direct_scatter_pair: bad plan a");
     const DirectPlanDev pa = direct_plan_dev(ws_a, n_a, rows_a);
     DirectPlanDev pb = pa;
@@ -976,7 +989,8 @@ int direct_scatter_pair(const int64_t* ids_a, int64_t n_a, int64_t rows_a, void*
     if (ga < 1) ga = 1;
     int gb = nb > 0 ? (int)((nb + kBT * 4 - 1) / (kBT * 4)) : 0;
     if (gb > cap) gb = cap;
-    k_direct_scatter_pair<<<ga + gb, kBT, 0, s>>>(ids_a, n_a, rows_a, pa, ga, ids_b, nb, rows_b, pb, err_flag);
+    k_direct_scatter_pair<<<ga + gb, kBT, 0, s>>>(ids_a, n_a, rows_a, pa, ga, ids_b, nb, rows_b, pb, err_flag, ignore_id,
+                                                  ignore_n);
     B2R_LAUNCH_OK("k_direct_scatter_pair");
     return 0;
 }
@@ -1029,4 +1043,34 @@ static int make_job_direct(const b2r_apply_job* j, int d, int mode, const b2r_op
     if (need > grid_cap) need = grid_cap;
     out->grid = (int)(need < 1 ? 1 : need);
     return 0;
+}
+
+// ---- C ABI of the direct plans for callers outside a step context (the autograd nodes, the shard owners) -------------
+extern "C" size_t b2r_direct_plan_workspace_bytes(int64_t n, int64_t n_rows) { return direct_workspace_bytes(n, n_rows); }
+
+extern "C" int b2r_direct_plan_init(void* ws, size_t ws_bytes, int64_t n, int64_t n_rows, b2r_stream_t stream) {
+    return direct_workspace_init(ws, ws_bytes, n, n_rows, as_stream(stream));
+}
+
+extern "C" int b2r_direct_plan_build(const int64_t* ids, int64_t n, int64_t n_rows, int64_t ignore_id, int64_t ignore_n,
+                                     void* ws, size_t ws_bytes, int32_t* err_flag, b2r_stream_t stream) {
+    B2R_REQUIRE(ids && ws, B2R_E_BADARG, "b2r_direct_plan_build: null pointer");
+    const size_t need = direct_workspace_bytes(n, n_rows);
+    B2R_REQUIRE(need != 0, B2R_E_UNSUPPORTED, "b2r_direct_plan_build: n=%lld n_rows=%lld unsupported", (long long)n,
+                (long long)n_rows);
+    B2R_REQUIRE(ws_bytes >= need, B2R_E_WORKSPACE, "b2r_direct_plan_build: workspace %zu < %zu", ws_bytes, need);
+    cudaStream_t s = as_stream(stream);
+    // a plan that was built but never applied leaves its spill counter set: clear the four counters here
+    const DirectPlanDev P = direct_plan_dev(ws, n, n_rows);
+    B2R_CUDA_OK(cudaMemsetAsync(P.counters, 0, 16, s));
+    int rc = direct_scatter_pair_ex(ids, n, n_rows, ws, nullptr, 0, 0, nullptr, err_flag, ignore_id, ignore_n, s);
+    if (rc != 0) return rc;
+    return direct_sort_pair(ws, n, n_rows, nullptr, 0, 0, s);
+}
+
+extern "C" int b2r_direct_plan_apply(const void* ws, int64_t n, int64_t n_rows, int d, const b2r_grad_source* s0,
+                                     const b2r_grad_source* s1, int mode, float* dense, float* W, float* m, float* v,
+                                     const b2r_optim* opt, b2r_stream_t stream) {
+    const b2r_apply_job j{ws, n, n_rows, s0, s1, dense, W, m, v};
+    return direct_apply_pair(&j, nullptr, d, mode, opt, as_stream(stream));
 }

@@ -453,9 +453,64 @@ class BucketPlan:
         self._apply(W.shape[1], sources, 2, W=W, m=m, v=v, opt=opt)
 
 
+_direct_ws = {}
+
+
+class DirectPlan:
+    """b2r_direct_plan_build / _apply: BucketPlan's job in two launches (scatter into fixed-capacity bucket regions + one
+    sort), same apply kernel.  Workspace cached per (device, stream, n, n_rows) and reused in stream order."""
+
+    def __init__(self, ids: torch.Tensor, n_rows: int, ignore_id: int = -1, ignore_n: int = 0):
+        _need_cuda(ids)
+        ids = _i64c(ids.reshape(-1), "ids")
+        n = ids.numel()
+        if n == 0:
+            raise ValueError("empty id list")
+        self.n, self.n_rows, self.device = n, int(n_rows), ids.device
+        L = _lib.load()
+        key = (ids.device.index, _stream(), n, self.n_rows)
+        ws = _direct_ws.get(key)
+        if ws is None:
+            nbytes = L.b2r_direct_plan_workspace_bytes(n, self.n_rows)
+            if nbytes == 0:
+                raise _lib.B200RecError(f"b2r_direct_plan_workspace_bytes({n}, {n_rows}) = 0")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
+            _lib.check(L.b2r_direct_plan_init(_p(ws), nbytes, n, self.n_rows, _stream()), "b2r_direct_plan_init")
+            _direct_ws[key] = ws
+        self.ws, self._ids = ws, ids
+        _lib.check(L.b2r_direct_plan_build(_p(ids), n, self.n_rows, int(ignore_id), int(ignore_n), _p(ws), ws.numel(),
+                                           _p(err_flag(ids.device)), _stream()), "b2r_direct_plan_build")
+
+    @staticmethod
+    def available(n: int, n_rows: int) -> bool:
+        return _lib.load().b2r_direct_plan_workspace_bytes(int(n), int(n_rows)) != 0
+
+    def _apply(self, d, sources, mode, dense=None, W=None, m=None, v=None, opt=None):
+        if not 1 <= len(sources) <= 2:
+            raise ValueError("one or two sources")
+        s0 = sources[0].c_struct()
+        s1 = sources[1].c_struct() if len(sources) == 2 else None
+        _lib.check(_lib.load().b2r_direct_plan_apply(_p(self.ws), self.n, self.n_rows, d, C.byref(s0),
+                                                     C.byref(s1) if s1 is not None else None, mode, _p(dense), _p(W), _p(m),
+                                                     _p(v), C.byref(opt) if opt is not None else None, _stream()),
+                   "b2r_direct_plan_apply")
+
+    def add_to_dense(self, dense: torch.Tensor, sources: Sequence[Source]) -> None:
+        self._apply(dense.shape[1], sources, 1, dense=dense)
+
+    def apply_optimizer(self, W: torch.Tensor, m, v, opt: _lib.Optim, sources: Sequence[Source]) -> None:
+        self._apply(W.shape[1], sources, 2, W=W, m=m, v=v, opt=opt)
+
+
+_PLAN_KIND = os.environ.get("B2R_PLAN", "direct")      # direct | bucket (A/B)
+
+
 def make_plan(ids: torch.Tensor, n_rows: int, d: int, ignore_id: int = -1, ignore_n: int = 0):
-    """BucketPlan where the bucket kernels exist (d = 32/64/128), IndexPlan (device radix sort) otherwise"""
+    """DirectPlan (two launches) where the bucket kernels exist (d = 32/64/128), IndexPlan (device radix sort) otherwise;
+    B2R_PLAN=bucket selects the four-launch BucketPlan for A/B runs"""
     if d in BucketPlan.SUPPORTED_D:
+        if _PLAN_KIND == "direct" and DirectPlan.available(ids.numel(), n_rows):
+            return DirectPlan(ids, n_rows, ignore_id, ignore_n)
         return BucketPlan(ids, n_rows, ignore_id, ignore_n)
     return IndexPlan(ids, n_rows, ignore_id, ignore_n)
 
