@@ -253,6 +253,14 @@ B2R_API int b2r_linear_bwd_weight(const float* dY, int lddy, const float* relu_o
                           float* dW, float* dbias, int64_t M, int N, int K, void* ws, size_t ws_bytes,
                           b2r_stream_t stream);
 
+/* The same weight gradient on the tcgen05 tensor cores (kind::tf32 with a hi/lo operand split, accumulator in TMEM; the
+ * batch-row index is the MMA's reduction dimension, activations are transposed on their way into shared memory).
+ * Shape class: N % 4 == 0, N <= 128, K % 16 == 0, K <= 240; returns B2R_E_UNSUPPORTED otherwise. */
+B2R_API size_t b2r_linear_bwd_weight_tc_workspace_bytes(int64_t M, int N, int K);
+B2R_API int b2r_linear_bwd_weight_tc(const float* dY, int lddy, const float* relu_out, const float* X, int ldx,
+                                     float* dW, float* dbias, int64_t M, int N, int K, void* ws, size_t ws_bytes,
+                                     b2r_stream_t stream);
+
 /* y = LayerNorm(x + res) * gamma + beta, eps inside the sqrt, biased variance (utils/layers.py:113,117 via
  * nn.LayerNorm); mean/rstd [rows] are saved for the backward.  Backward returns dz (gradient of x + res, to be
  * used for both addends) and dgamma/dbeta (fixed-order two-stage reduction).  d <= 256 in the backward. */

@@ -126,6 +126,18 @@ k_pair_runs_sum(const int64_t* __restrict__ key, const int64_t* __restrict__ row
                 in_run >>= start;
                 const int len = (~in_run == 0u) ? 32 - start : __ffs(~in_run) - 1;   // consecutive members from `start`
                 int t = start;
+                for (; t + 8 <= start + len; t += 8) {                      // 8 row loads in flight, added in order
+                    float4 x[8];
+                    float c[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t r = __shfl_sync(gmask, c_row, t + u, LPR);
+                        c[u] = __shfl_sync(gmask, c_coef, t + u, LPR);
+                        x[u] = ld_row4(T + (r < n_t ? r : 0) * D + sub * 4);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) fma4(acc, c[u], x[u]);
+                }
                 for (; t + 4 <= start + len; t += 4) {                      // 4 row loads in flight, added in order
                     float4 x[4];
                     float c[4];

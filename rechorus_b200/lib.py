@@ -97,6 +97,10 @@ SIGNATURES = {
     "b2r_linear_bwd_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                         C.c_void_p]),
+    "b2r_linear_bwd_weight_tc_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "b2r_linear_bwd_weight_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                           C.c_void_p]),
     "b2r_add_layernorm_fwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int64, C.c_int, C.c_float, C.c_void_p]),
     "b2r_add_layernorm_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "b2r_add_layernorm_bwd": (C.c_int, [C.c_void_p] * 9 + [C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -839,6 +839,15 @@ def linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, y_relu: Optio
     if need_dw or need_db:
         dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
         db = torch.empty((N,), dtype=torch.float32, device=dy.device) if need_db else None
+        if _TC_DW and M >= 4096 and N % 4 == 0 and N <= 128 and K % 16 == 0 and K <= 240 and lddy % 4 == 0 and ldx % 4 == 0:
+            # long reductions (M = B*L rows) on the tcgen05 tensor cores: k_linear_dw_tc
+            ws = _ws(L.b2r_linear_bwd_weight_tc_workspace_bytes(M, N, K), dy.device)
+            rc = L.b2r_linear_bwd_weight_tc(_p(dy), lddy, _p(y_relu), _p(x), ldx, _p(dW), _p(db), M, N, K, _p(ws), ws.numel(),
+                                            _stream())
+            if rc == 0:
+                return dx, dW, db
+            if rc != -3:                                   # B2R_E_UNSUPPORTED falls through to the CUDA-core kernel
+                _lib.check(rc, "b2r_linear_bwd_weight_tc")
         nbytes = L.b2r_linear_bwd_weight_workspace_bytes(M, N, K)
         ws = _ws(nbytes, dy.device)
         _lib.check(L.b2r_linear_bwd_weight(_p(dy), lddy, _p(y_relu), _p(x), ldx, _p(dW), _p(db), M, N, K, _p(ws),
@@ -849,6 +858,8 @@ def linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, y_relu: Optio
 # opt-in: run every Linear forward of the dense models on the tcgen05 kernel (verified to fp32-class accuracy in
 # tests/test_gpu_tc.py, currently ~10 % slower than the SGEMM at K = 64 -- DESIGN.md §6); off unless B2R_TC_LINEAR=1
 _TC_LINEAR = os.environ.get("B2R_TC_LINEAR") == "1"
+# weight gradients with a long batch reduction run on the tensor cores (csrc/linear_dw_tc.cu); B2R_TC_DW=0: CUDA cores
+_TC_DW = os.environ.get("B2R_TC_DW", "1") != "0"
 
 
 class _Linear(torch.autograd.Function):
