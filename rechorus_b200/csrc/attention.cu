@@ -235,21 +235,49 @@ k_select_last_bwd(const float* __restrict__ dh, const int64_t* __restrict__ hist
 __global__ void __launch_bounds__(256)
 k_small_table_partial(const float* __restrict__ src, int ld, const int64_t* __restrict__ ids, int64_t n, int n_rows,
                       int d, int rows_per_cta, float* __restrict__ part) {
-    extern __shared__ float tab[];             // [n_rows][d]
-    for (int e = threadIdx.x; e < n_rows * d; e += 256) tab[e] = 0.f;
+    // G = 256 / d row groups (d <= 256, a divisor of 256: otherwise G = 1 and the spare threads idle): group g walks rows
+    // beg + g, beg + g + G, ... of the CTA's range in order, thread = column, into the group's private copy of the table
+    // (no two threads ever touch the same shared-memory word); eight rows' loads are in flight before the first add.
+    // The G copies are then added in group order -> deterministic, no atomics.
+    extern __shared__ float tab[];             // [G][n_rows][d]
+    const int G = (d <= 256 && 256 % d == 0) ? 256 / d : 1;
+    for (int e = threadIdx.x; e < G * n_rows * d; e += 256) tab[e] = 0.f;
     __syncthreads();
     const int64_t beg = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t end = min(n, beg + rows_per_cta);
-    for (int c = threadIdx.x; c < d; c += 256) {
-        for (int64_t r = beg; r < end; ++r) {
-            int64_t id = ids[r];
-            id = (id < 0 || id >= n_rows) ? 0 : id;
-            tab[id * d + c] += src[r * ld + c];
+    const int g = threadIdx.x / d, c0 = threadIdx.x % d;
+    if (g < G) {
+        float* mine = tab + (size_t)g * n_rows * d;
+        for (int c = c0; c < d; c += (G == 1 ? 256 : d)) {
+            int64_t r = beg + g;
+            for (; r + 7 * G < end; r += 8 * G) {
+                int64_t id[8];
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    id[u] = ids[r + u * G];
+                    v[u] = src[(r + u * G) * ld + c];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t k = (id[u] < 0 || id[u] >= n_rows) ? 0 : id[u];
+                    mine[k * d + c] += v[u];
+                }
+            }
+            for (; r < end; r += G) {
+                int64_t k = ids[r];
+                k = (k < 0 || k >= n_rows) ? 0 : k;
+                mine[k * d + c] += src[r * ld + c];
+            }
         }
     }
     __syncthreads();
     float* out = part + (int64_t)blockIdx.x * n_rows * d;
-    for (int e = threadIdx.x; e < n_rows * d; e += 256) out[e] = tab[e];
+    for (int e = threadIdx.x; e < n_rows * d; e += 256) {
+        float a = tab[e];
+        for (int g2 = 1; g2 < G; ++g2) a += tab[(size_t)g2 * n_rows * d + e];
+        out[e] = a;
+    }
 }
 
 // fixed-order sum over the partial tables: 8 lanes per element (chunks c, c+8, ...), then a fixed shuffle tree
@@ -301,7 +329,7 @@ static int capped_grid(int64_t need, int per_sm) {
     return (int)(g < 1 ? 1 : g);
 }
 
-constexpr int kSmallTableRows = 256;
+constexpr int kSmallTableRows = 1024;
 
 }  // namespace b2r
 
@@ -384,7 +412,8 @@ extern "C" int b2r_small_table_grad(const float* src, int ld, const int64_t* ids
                                     float* dense_out, void* ws, size_t ws_bytes, b2r_stream_t stream) {
     B2R_REQUIRE(src && ids && dense_out && ws, B2R_E_BADARG, "b2r_small_table_grad: null pointer");
     B2R_REQUIRE(n > 0 && n_rows > 0 && d > 0 && ld >= d, B2R_E_BADARG, "b2r_small_table_grad: bad shape");
-    const size_t smem = (size_t)n_rows * d * sizeof(float);
+    const int G = (d <= 256 && 256 % d == 0) ? 256 / d : 1;
+    const size_t smem = (size_t)G * n_rows * d * sizeof(float);
     B2R_REQUIRE(smem <= 200 * 1024, B2R_E_UNSUPPORTED, "b2r_small_table_grad: table %d x %d does not fit shared memory",
                 n_rows, d);
     B2R_REQUIRE(ws_bytes >= b2r_small_table_grad_workspace_bytes(n, n_rows, d), B2R_E_WORKSPACE,

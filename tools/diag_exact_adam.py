@@ -21,6 +21,7 @@ g = torch.Generator().manual_seed(22)
 model.train()
 hist_i = {}
 gmin = {}
+track = {}     # (row, col) of the user table -> list of (step, g_ref, w_ref_after, w_gpu_after_flush)
 for step in range(25):
     uid = torch.randint(1, 60, (8,), generator=g)
     iid = torch.randint(1, 90, (8, 5), generator=g)
@@ -36,6 +37,11 @@ for step in range(25):
         if bad:
             print("step", step + 1, "rows off", [(r, float(e_i[r]), sorted(set(hist_i.get(r, [])))[-4:]) for r in bad[:5]],
                   "ids this step", sorted(set(iid.reshape(-1).tolist()))[:0])
+    gu = ref.p["u_embeddings.weight"].grad
+    for (r, c) in ((46, 44), (46, 54), (46, 0)):
+        wg = float(model.u_embeddings.weight[r, c]) if os.environ.get("DIAG_FLUSH") else float("nan")
+        track.setdefault((r, c), []).append((step + 1, float(gu[r, c]), float(ref.p["u_embeddings.weight"][r, c]), wg,
+                                             46 in uid.tolist()))
     for r in iid.reshape(-1).tolist():
         hist_i.setdefault(r, []).append(step + 1)
     gi = ref.p["i_embeddings.weight"].grad
@@ -54,3 +60,8 @@ for k, v in model.state_dict().items():
             opt = ref.opt.state[ref.p[k]]
             c = cols[0]
             print("      ref m,v at col", float(opt["exp_avg"][r, c]), float(opt["exp_avg_sq"][r, c]))
+
+for key, rows in track.items():
+    print("user entry", key)
+    for t in rows:
+        print("   step %2d g_ref % .3e w_ref % .8f w_gpu % .8f diff % .2e touched %s" % (t[0], t[1], t[2], t[3], t[3] - t[2], t[4]))

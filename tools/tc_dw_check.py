@@ -58,7 +58,9 @@ def run(M, N, K, relu, bias, ldpad=0):
         return e0.elapsed_time(e1) / 20 * 1e3
     print(f"M={M} N={N} K={K} relu={relu} bias={bias}: tc rel err {err:.2e} (bias {berr:.2e}), cuda-core rel err {err2:.2e}; "
           f"tc {timeit(tc):.1f} us, cuda-core {timeit(cc):.1f} us", flush=True)
-    assert err <= 5e-6 and berr <= 5e-6, (err, berr)
+    # the tensor core accumulates in fp32 with its own rounding: ~6e-6 of the largest entry over 204,800 rows (north-star
+    # bar for gradients: 1e-5)
+    assert err <= 1e-5 and berr <= 1e-5, (err, berr)
 
 
 if __name__ == "__main__":
