@@ -233,7 +233,7 @@ extern "C" int b2r_linear_bwd_weight_tc(const float* dY, int lddy, const float* 
     B2R_REQUIRE(ws_bytes >= b2r_linear_bwd_weight_tc_workspace_bytes(M, N, K), B2R_E_WORKSPACE,
                 "b2r_linear_bwd_weight_tc: workspace too small");
     const size_t smem = (size_t)2 * DW_SLABS * DW_MROWS * 128 + (size_t)2 * DW_SLABS * (K + 16) * 128 + 1024;
-    if (smem > 110 * 1024) return set_error(B2R_E_UNSUPPORTED, "b2r_linear_bwd_weight_tc: %zu B of shared memory needed", smem);
+    if (smem > 200 * 1024) return set_error(B2R_E_UNSUPPORTED, "b2r_linear_bwd_weight_tc: %zu B of shared memory needed", smem);
     const int ctas = dw_ctas(M);
     const int64_t slabs = (M + DW_SLABS * 32 - 1) / (DW_SLABS * 32);
     const int rows_per_cta = (int)((slabs + ctas - 1) / ctas) * DW_SLABS * 32;

@@ -73,11 +73,13 @@ def test_exact_adam_mode_reproduces_dense_adam_training(l2):
     ref = O.ReferenceStyleTrainer("BPRMF", w0, lr=1e-2, l2=l2, optimizer="Adam")
     g = torch.Generator().manual_seed(22)
     model.train()
-    # Adam's step lr * m_hat / (sqrt(v_hat) + 1e-8) is ill-conditioned for entries whose gradient is within a few orders of
-    # eps: du/dg ~ lr * eps / (|g| + eps)^2 turns a 1e-10 rounding difference in g (two correct fp32 evaluations of a
-    # cancelling expression) into ~1e-4 of weight.  Such entries exist without weight decay (a candidate with a ~0 softmax
-    # weight has a ~1e-8 gradient ROW); they are tracked on the reference side and judged by a looser bound.
-    min_g = {k: torch.full_like(v, float("inf")) for k, v in w0.items()}
+    # Without weight decay the comparison is CHAOTIC at the 1e-4 level, for torch.optim on two machines as much as for
+    # these kernels: Adam's step lr * m_hat / (sqrt(v_hat) + 1e-8) turns a 1e-10 rounding difference in a gradient entry
+    # that is within a few orders of eps (a candidate with a ~0 softmax weight has a ~1e-8 gradient ROW) into ~1e-4 of
+    # weight; that perturbed item row then enters the user gradients sum_c g_c * I[c], and where those cancel (|dU| ~ 1e-3
+    # from terms ~1e-2) a 7e-5 perturbation is ~1 % of the entry -- which Adam's normalisation again amplifies
+    # (traced entry by entry with tools/diag_exact_adam.py).  With weight decay every gradient entry carries l2 * w >> eps
+    # and the run is compared at 2e-5.
     for step in range(25):
         uid = torch.randint(1, 60, (8,), generator=g)
         iid = torch.randint(1, 90, (8, 5), generator=g)
@@ -88,19 +90,13 @@ def test_exact_adam_mode_reproduces_dense_adam_training(l2):
         model.optimizer.step()
         ref_loss = ref.step({"user_id": uid, "item_id": iid}, shuffle=False)
         assert abs(float(loss) - ref_loss) <= 2e-5, (step, float(loss), ref_loss)
-        for k in min_g:
-            gk = ref.p[k].grad.abs()
-            min_g[k] = torch.where(gk > 0, torch.minimum(min_g[k], gk), min_g[k])
     model.optimizer.flush()
     for k, v in model.state_dict().items():
         err = (v.cpu() - ref.p[k].detach()).abs()
         if l2 > 0:
-            assert float(err.max()) <= 2e-5, (k, float(err.max()))      # g + l2 * w >> eps everywhere: well-conditioned
-            continue
-        well = min_g[k] > 1e-5                              # includes never-touched entries (inf)
-        assert float(err[well].max()) <= 2e-5, (k, float(err[well].max()))
-        assert float(err.max()) <= 1e-3, (k, float(err.max()))
-        assert float(well.float().mean()) > 0.9             # the yardstick covers nearly everything
+            assert float(err.max()) <= 2e-5, (k, float(err.max()))
+        else:
+            assert float(err.max()) <= 2e-4 and float(err.reshape(-1).quantile(0.9)) <= 2e-6, (k, float(err.max()))
 
 
 def test_device_negative_sampler_equals_its_cpu_definition_bit_for_bit():
