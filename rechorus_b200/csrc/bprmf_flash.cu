@@ -22,7 +22,7 @@
 // (ST - 1) * RCH rows per group are always in flight; each lane reads back only the 16 bytes it copied itself.  The
 // sample's ids are fetched first (one coalesced pass) and parked in shared memory as checked 32-bit row indices.  The
 // groups' partial states meet once per sample through shuffles (online-softmax combine, fixed order -> deterministic).
-// All 8 warps x 4 CTAs per SM of a B = 4096 batch are resident at once: a single wave, no tail.
+// All 7 warps x 4 CTAs per SM of a B = 4096 batch are resident at once: a single wave, no tail.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -30,7 +30,7 @@
 
 namespace b2r {
 
-constexpr int kFlWarps = 8;
+constexpr int kFlMaxWarps = 8;
 
 // sum each of the RCH per-lane values over the LPR lanes of a group with ~RCH + log2(LPR / RCH) shuffles: at every step
 // the lanes split the live values in two halves and exchange the half they give up.  Afterwards lane `sub` holds the
@@ -77,8 +77,11 @@ __device__ __forceinline__ void fl_cp16(void* smem_dst, const void* gsrc, bool v
 // ST ring stages.  Per warp the ring holds ST * RCH * (32 / LPR) rows = ST * RCH * VPL * 512 bytes.
 // PLAN: also drop every (row, position) pair of the batch into the update's index plan (plan_direct.cuh) while the ids
 // pass through -- the step then needs no partition pass of its own.
-template <int D, int VPL, int RCH, int ST, bool PLAN>
-__global__ void __launch_bounds__(kFlWarps * 32, (ST * RCH * VPL <= 12) ? 4 : 2)
+// WPC warps (= samples in flight) per CTA: 7 x 4 CTAs per SM hold a B = 4096 batch in one wave (586 CTAs <= 592 slots) and
+// leave ~34 KB of shared memory and 8 K registers per SM for the plan kernels of the side stream; with 8 the forward
+// kernel takes all of an SM's shared memory and any co-resident CTA pushes a quarter of its samples into a second wave.
+template <int D, int VPL, int RCH, int ST, bool PLAN, int WPC>
+__global__ void __launch_bounds__(WPC * 32, (ST * RCH * VPL <= 12) ? 4 : 2)
 k_bprmf_flash(const float* __restrict__ U, const int64_t* __restrict__ uid, int64_t n_users,
               const float* __restrict__ T, const int64_t* __restrict__ ids, int64_t n_t,
               float* __restrict__ pred, float* __restrict__ gout, float* __restrict__ row_loss,
@@ -106,7 +109,7 @@ k_bprmf_flash(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
         plan_u.counters[1] = plan_u.counters[2] = plan_u.counters[3] = 0;
     }
 
-    for (int64_t b = (int64_t)blockIdx.x * kFlWarps + warp; b < B; b += (int64_t)gridDim.x * kFlWarps) {
+    for (int64_t b = (int64_t)blockIdx.x * WPC + warp; b < B; b += (int64_t)gridDim.x * WPC) {
         // ---- ids of the sample: one coalesced pass, range-checked once, parked as 32-bit row indices -------------
         const int64_t* idp = ids + b * C;
         for (int c = lane; c < C; c += 32) {
@@ -286,7 +289,7 @@ k_bprmf_flash(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
     // mean of the per-sample losses by the last CTA to finish (fixed summation order -> deterministic)
     if (loss_out != nullptr) {
         __shared__ bool last;
-        __shared__ float red[kFlWarps * 32];
+        __shared__ float red[256];
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
@@ -294,10 +297,11 @@ k_bprmf_flash(const float* __restrict__ U, const int64_t* __restrict__ uid, int6
         if (last) {
             __threadfence();
             float a = 0.f;
-            for (int i = threadIdx.x; i < B; i += kFlWarps * 32) a += __ldcg(row_loss + i);
+            for (int i = threadIdx.x; i < B; i += WPC * 32) a += __ldcg(row_loss + i);
             red[threadIdx.x] = a;
+            for (int i = WPC * 32 + threadIdx.x; i < 256; i += WPC * 32) red[i] = 0.f;
             __syncthreads();
-            for (int o = kFlWarps * 16; o > 0; o >>= 1) {
+            for (int o = 128; o > 0; o >>= 1) {
                 if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
                 __syncthreads();
             }
@@ -323,7 +327,9 @@ int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, 
         (int64_t)B * C >= 0xffffffffLL)
         return set_error(B2R_E_UNSUPPORTED, "bprmf_flash: d=%d C=%d", d, C);
     const int cpad = (C + 3) / 4 * 4;
-    const int64_t need = ((int64_t)B + kFlWarps - 1) / kFlWarps;
+    // B2R_FLASH_WARPS=8 (A/B): 8 samples per CTA instead of 7
+    static const int wpc = [] { const char* e = getenv("B2R_FLASH_WARPS"); return (e && atoi(e) == 8) ? 8 : 7; }();
+    const int64_t need = ((int64_t)B + wpc - 1) / wpc;
     const int64_t cap = (int64_t)sm_count() * 32;                         // beyond that, warps loop over samples
     const int grid = (int)(need < cap ? need : cap);
     const bool plan = plan_i != nullptr && plan_u != nullptr;
@@ -333,18 +339,22 @@ int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, 
     // 3 stages: 0.1501 ms per config-2 step); 223 / 243 (two float4 per lane) execute fewer instructions but spill under
     // the 64-register cap the single-wave residency needs and measure 0.152 ms (profiles/README r2).
     static const int variant = [] { const char* e = getenv("B2R_FLASH"); return e ? atoi(e) : 143; }();
-#define B2R_FL(D_, VPL, RCH, ST, PLAN)                                                                               \
+#define B2R_FLW(D_, VPL, RCH, ST, PLAN, WPC)                                                                         \
     do {                                                                                                             \
-        const int smem = kFlWarps * (ST * RCH * VPL * 32 * 16 + cpad * 8);                                           \
+        const int smem = WPC * (ST * RCH * VPL * 32 * 16 + cpad * 8);                                                \
         static int attr_smem = 0;                                                                                    \
         if (smem > attr_smem) {                                                                                      \
-            B2R_CUDA_OK(cudaFuncSetAttribute(k_bprmf_flash<D_, VPL, RCH, ST, PLAN>,                                  \
+            B2R_CUDA_OK(cudaFuncSetAttribute(k_bprmf_flash<D_, VPL, RCH, ST, PLAN, WPC>,                             \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
             attr_smem = smem;                                                                                        \
         }                                                                                                            \
-        k_bprmf_flash<D_, VPL, RCH, ST, PLAN><<<grid, kFlWarps * 32, smem, as_stream(stream)>>>(                     \
+        k_bprmf_flash<D_, VPL, RCH, ST, PLAN, WPC><<<grid, WPC * 32, smem, as_stream(stream)>>>(                     \
             U, uid, n_users, I, iid, n_items, pred, grad_pred, row_loss, dQ, qout, B, C, cpad, err_flag, loss_out,   \
             done_counter, pi, pu);                                                                                   \
+    } while (0)
+#define B2R_FL(D_, VPL, RCH, ST, PLAN)                                                                               \
+    do {                                                                                                             \
+        if (wpc == 8) B2R_FLW(D_, VPL, RCH, ST, PLAN, 8); else B2R_FLW(D_, VPL, RCH, ST, PLAN, 7);                   \
     } while (0)
 #define B2R_FL_V(D_, PLAN)                                                                                           \
     do {                                                                                                             \
@@ -362,6 +372,7 @@ int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, 
 #undef B2R_FL_D
 #undef B2R_FL_V
 #undef B2R_FL
+#undef B2R_FLW
     B2R_LAUNCH_OK("k_bprmf_flash");
     return 0;
 }

@@ -124,7 +124,10 @@ extern "C" int b2r_bprmf_ctx_create(void** ctx_out, int B, int C, int d, int64_t
     // the next batch is starved and the next step's update waits for it (measured: 0.177 vs 0.199 ms per step).
     int prio_lo = 0, prio_hi = 0;
     cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi);
+    // B2R_SIDE_PRIO=low (A/B knob): plan stream at the lowest priority instead
+    const char* sp = getenv("B2R_SIDE_PRIO");
+    const int side_prio = (sp && sp[0] == 'l') ? prio_lo : prio_hi;
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, side_prio);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->join[1], cudaEventDisableTiming);
