@@ -22,7 +22,7 @@
 // (ST - 1) * RCH rows per group are always in flight; each lane reads back only the 16 bytes it copied itself.  The
 // sample's ids are fetched first (one coalesced pass) and parked in shared memory as checked 32-bit row indices.  The
 // groups' partial states meet once per sample through shuffles (online-softmax combine, fixed order -> deterministic).
-// All 7 warps x 4 CTAs per SM of a B = 4096 batch are resident at once: a single wave, no tail.
+// All 8 warps x 4 CTAs per SM of a B = 4096 batch are resident at once: a single wave, no tail.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -77,9 +77,8 @@ __device__ __forceinline__ void fl_cp16(void* smem_dst, const void* gsrc, bool v
 // ST ring stages.  Per warp the ring holds ST * RCH * (32 / LPR) rows = ST * RCH * VPL * 512 bytes.
 // PLAN: also drop every (row, position) pair of the batch into the update's index plan (plan_direct.cuh) while the ids
 // pass through -- the step then needs no partition pass of its own.
-// WPC warps (= samples in flight) per CTA: 7 x 4 CTAs per SM hold a B = 4096 batch in one wave (586 CTAs <= 592 slots) and
-// leave ~34 KB of shared memory and 8 K registers per SM for the plan kernels of the side stream; with 8 the forward
-// kernel takes all of an SM's shared memory and any co-resident CTA pushes a quarter of its samples into a second wave.
+// WPC warps (= samples in flight) per CTA: 8 (default; 512 CTAs, 4 per SM, take all of an SM's shared memory) or 7 (586
+// CTAs, leave ~34 KB of shared memory per SM for co-resident plan CTAs of the side stream -- measured slower in the step).
 template <int D, int VPL, int RCH, int ST, bool PLAN, int WPC>
 __global__ void __launch_bounds__(WPC * 32, (ST * RCH * VPL <= 12) ? 4 : 2)
 k_bprmf_flash(const float* __restrict__ U, const int64_t* __restrict__ uid, int64_t n_users,
@@ -327,8 +326,9 @@ int b2r_bprmf_flash_launch(const float* U, const int64_t* uid, int64_t n_users, 
         (int64_t)B * C >= 0xffffffffLL)
         return set_error(B2R_E_UNSUPPORTED, "bprmf_flash: d=%d C=%d", d, C);
     const int cpad = (C + 3) / 4 * 4;
-    // B2R_FLASH_WARPS=8 (A/B): 8 samples per CTA instead of 7
-    static const int wpc = [] { const char* e = getenv("B2R_FLASH_WARPS"); return (e && atoi(e) == 8) ? 8 : 7; }();
+    // B2R_FLASH_WARPS=7 (A/B): 7 samples per CTA instead of 8 (leaves shared memory for co-resident plan CTAs; measured
+    // slower: 0.159 vs 0.151 ms per config-2 step)
+    static const int wpc = [] { const char* e = getenv("B2R_FLASH_WARPS"); return (e && atoi(e) == 7) ? 7 : 8; }();
     const int64_t need = ((int64_t)B + wpc - 1) / wpc;
     const int64_t cap = (int64_t)sm_count() * 32;                         // beyond that, warps loop over samples
     const int grid = (int)(need < cap ? need : cap);
