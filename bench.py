@@ -403,6 +403,22 @@ def run_c2(args, rank, world, local_rank, sampler):
                                         "steps": n_s, "note": "plus BaseRunner.py:187-202: CPU rand+argsort of [B,C], "
                                         "index gather and index_put un-shuffle every step"}}
 
+    # ---- price of exact dense-Adam RESULTS from the row-sparse kernels (--exact_adam 1): same contract route, rows are
+    # advanced through the optimizer steps they skipped before every read -------------------------------------------------
+    try:
+        from rechorus_b200.optim import RowSparseOptimizer
+        lazy_opt = model.optimizer
+        model.optimizer = RowSparseOptimizer(model, "Adam", lr=1e-3, l2=0.0, exact_dense=True)
+        ms_exact, _, _ = timed_loop(dist, lambda k: contract_step(k, False), max(3, min(n_c, 60)), 3)
+        contract["exact_adam"] = {"ms_per_step": round(ms_exact, 5), "value": round(world * B * C / (ms_exact * 1e-3), 1),
+                                  "note": "RowSparseOptimizer(exact_dense=True): dense torch.optim.Adam results (rows advanced "
+                                          "through their skipped steps, b2r_adam_exact_advance) on the same contract route; "
+                                          "compare with contract_route.ms_per_step (lazy / SparseAdam semantics)"}
+        model.optimizer = lazy_opt
+        ops.check_ids(device)
+    except Exception as e:                                    # never let the extra leg take the headline down
+        contract["exact_adam"] = {"error": repr(e)[:200]}
+
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     peak, _, peak_src = measured_peaks()
     nu = statistics.mean(n_uniq[(args.warmup + k) % POOL] for k in range(args.steps))

@@ -289,7 +289,15 @@ B2R_API int b2r_attention_fwd(const float* q, const float* k, const float* v, in
                       int H, b2r_stream_t stream);
 B2R_API int b2r_attention_bwd(const float* q, const float* k, const float* v, int ld, const float* dctx, float* dq,
                       float* dk, float* dv, int ldg, int B, int L, int d, int H, b2r_stream_t stream);
-/* Groundwork, opt-in (B2R_SASREC_LASTQ=1), not used by the default paths of this round: attention for ONE query per
+/* The same with dead rows skipped: live[b] (int64, NULL = L) is the number of leading positions of sequence b whose
+ * output anything downstream reads -- SASRec uses position len-1 only (SASRec.py:74-81) and attention is causal, so the
+ * positions >= len are exact dead work (forward and backward).  Dead rows of ctx / dq / dk / dv are written as zeros. */
+B2R_API int b2r_attention_fwd_live(const float* q, const float* k, const float* v, int ld, const int64_t* live, float* ctx,
+                                   int B, int L, int d, int H, b2r_stream_t stream);
+B2R_API int b2r_attention_bwd_live(const float* q, const float* k, const float* v, int ld, const int64_t* live,
+                                   const float* dctx, float* dq, float* dk, float* dv, int ldg, int B, int L, int d, int H,
+                                   b2r_stream_t stream);
+/* Attention for ONE query per
  * sequence -- the query at position t* = clamp(lengths[b]-1, 0, L-1), the only position of SASRec's last block whose
  * output is used (models/sequential/SASRec.py:74-81) -- against keys/values 0..t* (the causal row of
  * utils/layers.py:52-63).  q_last, ctx_last, dq_last are [B, d]; k, v, dk, dv are [B, L, d] rows with leading

@@ -40,7 +40,7 @@ k_embed_hist(const float* __restrict__ I, int64_t n_items, const float* __restri
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_attention_fwd(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
-                float* __restrict__ ctx, int L, int d, int H, float scale) {
+                float* __restrict__ ctx, int L, int d, int H, float scale, const int64_t* __restrict__ live) {
     extern __shared__ float sm[];
     const int S = d + 1;                       // padded row stride: lanes index rows -> distinct banks
     float* qs = sm;                            // [L][S]
@@ -58,8 +58,16 @@ k_attention_fwd(const float* __restrict__ q, const float* __restrict__ k, const 
         vs[t * S + c] = v[g];
     }
     __syncthreads();
+    // live[b] (optional): rows t >= live[b] of this sequence are dead -- nothing downstream reads them (causal attention:
+    // SASRec uses position len-1 only, SASRec.py:74-81); their context is written as zeros and their work is skipped
+    int Lb = L;
+    if (live != nullptr) {
+        const int64_t lv = live[b];
+        Lb = lv < 0 ? 0 : (lv > L ? L : (int)lv);
+        for (int e = threadIdx.x; e < (L - Lb) * d; e += 256) ctx[((int64_t)b * L + Lb) * d + e] = 0.f;
+    }
     float* pw = ps + warp * H * L;
-    for (int i = warp; i < L; i += 8) {
+    for (int i = warp; i < Lb; i += 8) {
         for (int h = 0; h < H; ++h) {
             const float* qi = qs + i * S + h * dk;
             float mx = -INFINITY;
@@ -99,7 +107,7 @@ k_attention_fwd(const float* __restrict__ q, const float* __restrict__ k, const 
 __global__ void __launch_bounds__(256)
 k_attention_bwd(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v, int ld,
                 const float* __restrict__ dctx, float* __restrict__ dq, float* __restrict__ dk_, float* __restrict__ dv,
-                int ldg, int L, int d, int H, float scale) {
+                int ldg, int L, int d, int H, float scale, const int64_t* __restrict__ live) {
     extern __shared__ float sm[];
     const int S = d + 1;
     const int LP = L + 1;
@@ -120,13 +128,27 @@ k_attention_bwd(const float* __restrict__ q, const float* __restrict__ k, const 
         gs[t * S + c] = dctx[((int64_t)b * L + t) * d + c];
     }
     __syncthreads();
+    // dead rows (t >= live[b], see k_attention_fwd): their upstream gradient is zero by construction and so are the
+    // gradients they would receive; every phase below runs over the live rows only (Lq = live length)
+    int Lq = L;
+    if (live != nullptr) {
+        const int64_t lv = live[b];
+        Lq = lv < 0 ? 0 : (lv > L ? L : (int)lv);
+        for (int e = threadIdx.x; e < (L - Lq) * d; e += 256) {
+            const int t = Lq + e / d, c = e % d;
+            const int64_t g = ((int64_t)b * L + t) * ldg + c;
+            dq[g] = 0.f;
+            dk_[g] = 0.f;
+            dv[g] = 0.f;
+        }
+    }
     // phase A: probabilities (zero above the diagonal)
-    for (int i = warp; i < L; i += 8) {
+    for (int i = warp; i < Lq; i += 8) {
         for (int h = 0; h < H; ++h) {
             float* pr = P + ((int64_t)h * L + i) * LP;
             const float* qi = qs + i * S + h * dk;
             float mx = -INFINITY;
-            for (int j = lane; j < L; j += 32) {
+            for (int j = lane; j < Lq; j += 32) {
                 float s = -INFINITY;
                 if (j <= i) {
                     const float* kj = ks + j * S + h * dk;
@@ -139,28 +161,28 @@ k_attention_bwd(const float* __restrict__ q, const float* __restrict__ k, const 
             }
             mx = warp_max(mx);
             float z = 0.f;
-            for (int j = lane; j < L; j += 32) {
+            for (int j = lane; j < Lq; j += 32) {
                 const float e = (j <= i) ? expf(pr[j] - mx) : 0.f;
                 pr[j] = e;
                 z += e;
             }
             z = warp_sum(z);
             const float inv = 1.f / z;
-            for (int j = lane; j < L; j += 32) pr[j] *= inv;
+            for (int j = lane; j < Lq; j += 32) pr[j] *= inv;
         }
     }
     __syncthreads();
     // phase B: dV[j,c] = sum_{i>=j} P[h(c)][i][j] * dctx[i,c]
-    for (int e = threadIdx.x; e < L * d; e += 256) {
+    for (int e = threadIdx.x; e < Lq * d; e += 256) {
         const int j = e / d, c = e % d;
         const float* ph = P + (int64_t)(c / dk) * L * LP;
         float a = 0.f;
-        for (int i = j; i < L; ++i) a = fmaf(ph[i * LP + j], gs[i * S + c], a);
+        for (int i = j; i < Lq; ++i) a = fmaf(ph[i * LP + j], gs[i * S + c], a);
         dv[((int64_t)b * L + j) * ldg + c] = a;
     }
     __syncthreads();
     // phase C: dS = P * (dP - sum_j P dP) * scale, in place
-    for (int i = warp; i < L; i += 8) {
+    for (int i = warp; i < Lq; i += 8) {
         for (int h = 0; h < H; ++h) {
             float* pr = P + ((int64_t)h * L + i) * LP;
             const float* gi = gs + i * S + h * dk;
@@ -187,12 +209,12 @@ k_attention_bwd(const float* __restrict__ q, const float* __restrict__ k, const 
     }
     __syncthreads();
     // phase D: dQ[i,c] = sum_{j<=i} dS[h][i][j] k[j,c];  dK[j,c] = sum_{i>=j} dS[h][i][j] q[i,c]
-    for (int e = threadIdx.x; e < L * d; e += 256) {
+    for (int e = threadIdx.x; e < Lq * d; e += 256) {
         const int t = e / d, c = e % d;
         const float* ph = P + (int64_t)(c / dk) * L * LP;
         float aq = 0.f, ak = 0.f;
         for (int j = 0; j <= t; ++j) aq = fmaf(ph[t * LP + j], ks[j * S + c], aq);
-        for (int i = t; i < L; ++i) ak = fmaf(ph[i * LP + t], qs[i * S + c], ak);
+        for (int i = t; i < Lq; ++i) ak = fmaf(ph[i * LP + t], qs[i * S + c], ak);
         dq[((int64_t)b * L + t) * ldg + c] = aq;
         dk_[((int64_t)b * L + t) * ldg + c] = ak;
     }
@@ -352,8 +374,8 @@ static size_t attn_bwd_smem(int L, int d, int H) {
     return ((size_t)4 * L * (d + 1) + (size_t)H * L * (L + 1)) * sizeof(float);
 }
 
-extern "C" int b2r_attention_fwd(const float* q, const float* k, const float* v, int ld, float* ctx, int B, int L,
-                                 int d, int H, b2r_stream_t stream) {
+extern "C" int b2r_attention_fwd_live(const float* q, const float* k, const float* v, int ld, const int64_t* live, float* ctx,
+                                      int B, int L, int d, int H, b2r_stream_t stream) {
     B2R_REQUIRE(q && k && v && ctx, B2R_E_BADARG, "b2r_attention_fwd: null pointer");
     B2R_REQUIRE(B >= 0 && L > 0 && d > 0 && H > 0 && d % H == 0 && ld >= d, B2R_E_BADARG,
                 "b2r_attention_fwd: bad shape B=%d L=%d d=%d H=%d ld=%d", B, L, d, H, ld);
@@ -362,13 +384,19 @@ extern "C" int b2r_attention_fwd(const float* q, const float* k, const float* v,
     B2R_REQUIRE(smem <= 227 * 1024, B2R_E_UNSUPPORTED, "b2r_attention_fwd: L=%d d=%d needs %zu B of shared memory", L, d,
                 smem);
     B2R_CUDA_OK(cudaFuncSetAttribute(k_attention_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_attention_fwd<<<B, 256, smem, as_stream(stream)>>>(q, k, v, ld, ctx, L, d, H, 1.f / sqrtf((float)(d / H)));
+    k_attention_fwd<<<B, 256, smem, as_stream(stream)>>>(q, k, v, ld, ctx, L, d, H, 1.f / sqrtf((float)(d / H)), live);
     B2R_LAUNCH_OK("k_attention_fwd");
     return 0;
 }
 
-extern "C" int b2r_attention_bwd(const float* q, const float* k, const float* v, int ld, const float* dctx, float* dq,
-                                 float* dk, float* dv, int ldg, int B, int L, int d, int H, b2r_stream_t stream) {
+extern "C" int b2r_attention_fwd(const float* q, const float* k, const float* v, int ld, float* ctx, int B, int L,
+                                 int d, int H, b2r_stream_t stream) {
+    return b2r_attention_fwd_live(q, k, v, ld, nullptr, ctx, B, L, d, H, stream);
+}
+
+extern "C" int b2r_attention_bwd_live(const float* q, const float* k, const float* v, int ld, const int64_t* live,
+                                      const float* dctx, float* dq, float* dk, float* dv, int ldg, int B, int L, int d, int H,
+                                      b2r_stream_t stream) {
     B2R_REQUIRE(q && k && v && dctx && dq && dk && dv, B2R_E_BADARG, "b2r_attention_bwd: null pointer");
     B2R_REQUIRE(B >= 0 && L > 0 && L <= 128 && d > 0 && H > 0 && d % H == 0 && ld >= d && ldg >= d, B2R_E_BADARG,
                 "b2r_attention_bwd: bad shape B=%d L=%d d=%d H=%d", B, L, d, H);
@@ -378,9 +406,14 @@ extern "C" int b2r_attention_bwd(const float* q, const float* k, const float* v,
                 L, d, H, smem);
     B2R_CUDA_OK(cudaFuncSetAttribute(k_attention_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_attention_bwd<<<B, 256, smem, as_stream(stream)>>>(q, k, v, ld, dctx, dq, dk, dv, ldg, L, d, H,
-                                                        1.f / sqrtf((float)(d / H)));
+                                                        1.f / sqrtf((float)(d / H)), live);
     B2R_LAUNCH_OK("k_attention_bwd");
     return 0;
+}
+
+extern "C" int b2r_attention_bwd(const float* q, const float* k, const float* v, int ld, const float* dctx, float* dq,
+                                 float* dk, float* dv, int ldg, int B, int L, int d, int H, b2r_stream_t stream) {
+    return b2r_attention_bwd_live(q, k, v, ld, nullptr, dctx, dq, dk, dv, ldg, B, L, d, H, stream);
 }
 
 extern "C" int b2r_select_last(const float* y, const int64_t* hist, const int64_t* lengths, float* h, int B, int L,

@@ -936,34 +936,37 @@ def add_layernorm(x, res, gamma, beta, eps=1e-5):
 
 
 class _CausalAttention(torch.autograd.Function):
-    """layers.py:52-63 for q,k,v [B, L, d] with H heads (contiguous d/H chunks), causal mask, no W_o."""
+    """layers.py:52-63 for q,k,v [B, L, d] with H heads (contiguous d/H chunks), causal mask, no W_o.  ``live`` (optional
+    int64 [B]): positions >= live[b] are dead rows (nothing downstream reads them): skipped, written as zeros."""
 
     @staticmethod
-    def forward(ctx, q, k, v, H):
-        _need_cuda(q, k, v)
+    def forward(ctx, q, k, v, H, live):
+        _need_cuda(q, k, v, live)
         B, Ln, d = q.shape
         q, k, v = _f32c(q, "q"), _f32c(k, "k"), _f32c(v, "v")
+        live = None if live is None else _i64c(live, "live lengths")
         out = torch.empty((B, Ln, d), dtype=torch.float32, device=q.device)
         L = _lib.load()
-        _lib.check(L.b2r_attention_fwd(_p(q), _p(k), _p(v), d, _p(out), B, Ln, d, H, _stream()), "b2r_attention_fwd")
-        ctx.save_for_backward(q, k, v)
+        _lib.check(L.b2r_attention_fwd_live(_p(q), _p(k), _p(v), d, _p(live), _p(out), B, Ln, d, H, _stream()),
+                   "b2r_attention_fwd")
+        ctx.save_for_backward(q, k, v, live)
         ctx.H = H
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v = ctx.saved_tensors
+        q, k, v, live = ctx.saved_tensors
         B, Ln, d = q.shape
         dout = _f32c(dout, "dctx")
         dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
         L = _lib.load()
-        _lib.check(L.b2r_attention_bwd(_p(q), _p(k), _p(v), d, _p(dout), _p(dq), _p(dk), _p(dv), d, B, Ln, d, ctx.H,
-                                       _stream()), "b2r_attention_bwd")
-        return dq, dk, dv, None
+        _lib.check(L.b2r_attention_bwd_live(_p(q), _p(k), _p(v), d, _p(live), _p(dout), _p(dq), _p(dk), _p(dv), d, B, Ln, d,
+                                            ctx.H, _stream()), "b2r_attention_bwd")
+        return dq, dk, dv, None, None
 
 
-def causal_attention(q, k, v, num_heads):
-    return _CausalAttention.apply(q, k, v, num_heads)
+def causal_attention(q, k, v, num_heads, live=None):
+    return _CausalAttention.apply(q, k, v, num_heads, live)
 
 
 class _AttentionLast(torch.autograd.Function):

@@ -100,6 +100,30 @@ def test_causal_attention_forward_backward(B, L, d, H):
     _close(vc.grad, v.grad, 2e-5)
 
 
+@pytest.mark.parametrize("B,L,d,H", [(6, 50, 64, 4), (4, 33, 128, 8), (3, 7, 32, 2)])
+def test_causal_attention_with_dead_rows_skipped_equals_full_attention_on_the_live_rows(B, L, d, H):
+    """live[b] positions matter, the rest is dead work (SASRec reads position len-1 only and the mask is causal): the
+    live rows of the output and of dq/dk/dv equal the full computation's when the dead rows receive no upstream gradient;
+    dead rows come back as zeros"""
+    from rechorus_b200 import ops
+    g = torch.Generator().manual_seed(B + L)
+    q, k, v = [(torch.randn(B, L, d, generator=g)).requires_grad_(True) for _ in range(3)]
+    live = torch.randint(1, L + 1, (B,), generator=g)
+    live[0], live[-1] = L, 1
+    rowmask = (torch.arange(L).view(1, L) < live.view(B, 1)).unsqueeze(-1).float()
+    out = _ref_attention(q, k, v, H)
+    go = torch.randn(B, L, d, generator=g) * rowmask
+    out.backward(go)
+    qc, kc, vc = [t.detach().cuda().requires_grad_(True) for t in (q, k, v)]
+    oc = ops.causal_attention(qc, kc, vc, H, live=live.cuda())
+    oc.backward(go.cuda())
+    _close(oc, out * rowmask)
+    assert float((oc.cpu() * (1 - rowmask)).abs().max()) == 0.0
+    for a, b in ((qc.grad, q.grad), (kc.grad, k.grad), (vc.grad, v.grad)):
+        _close(a, b * rowmask, 2e-5)
+        assert float((a.cpu() * (1 - rowmask)).abs().max()) == 0.0
+
+
 def test_embed_history_and_small_table_gradient():
     from rechorus_b200 import ops
     g = torch.Generator().manual_seed(5)
