@@ -177,7 +177,8 @@ def build_model(w, device, extra=()):
     torch.manual_seed(0)
     n_users = w["n_users"] if w["model"] != "SASRec" else 10          # SASRec has no user table
     model = cls(a, types.SimpleNamespace(n_users=n_users, n_items=w["n_items"])).to(device)
-    model.optimizer = RowSparseOptimizer(model, "Adam", lr=1e-3, l2=0.0)     # reference defaults (BaseRunner.py:28-38)
+    model.optimizer = RowSparseOptimizer(model, "Adam", lr=1e-3, l2=0.0,     # reference defaults (BaseRunner.py:28-38)
+                                         device_clock=(w["model"] != "BPRMF"))
     model.train()
     return model, a
 
@@ -571,18 +572,19 @@ def run_model_steps(wname, args, rank, world, local_rank, sampler, steps_cap):
         return loss
 
     launches0 = lib.b2r_launch_count()
-    ms, loss, win = timed_loop(dist, step, steps, warmup)
+    ms_eager, loss, win = timed_loop(dist, step, steps, warmup)
     launches = (lib.b2r_launch_count() - launches0) * steps // (steps + warmup)
+    sampler.window(*win)
+    # the same step captured once in a CUDA graph and replayed (rechorus_b200.graph.GraphedStep): one host launch per step
+    from rechorus_b200.graph import GraphedStep
+    gstep = GraphedStep(model, feeds[0], warmup=2)
+    ms, loss, win = timed_loop(dist, lambda k: gstep(feeds[k % len(feeds)]), steps, warmup)
+    loss = loss.clone()
     sampler.window(*win)
 
     def step_e2e(k):
-        src = pinned[k % len(pinned)]
-        f = {k_: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k_, v in src.items()}
-        model.optimizer.zero_grad()
-        ls = model.loss(model(f))
-        ls.backward()
-        model.optimizer.step()
-        return float(ls.detach().cpu())               # the runner reads every step's loss (BaseRunner.py:207)
+        ls = gstep(pinned[k % len(pinned)])            # H2D of the batch into the graph's static buffers, replay
+        return float(ls)                               # the runner reads every step's loss (BaseRunner.py:207)
 
     ms_e2e, _, win = timed_loop(dist, step_e2e, steps, warmup)
     sampler.window(*win)
@@ -594,10 +596,13 @@ def run_model_steps(wname, args, rank, world, local_rank, sampler, steps_cap):
     h2d = sum(v.numel() * 8 for v in host[0].values())
     out = {"value": round(value, 1), "unit": UNIT, "ms_per_step": round(ms, 5), "steps": steps, "warmup": warmup,
            "config": {"workload": wname + ": " + w["desc"], "optimizer": "Adam lr=1e-3 (tables row-sparse/lazy, dense parameters exact)",
-                      "route": "forward -> loss -> backward -> optimizer.step() through the plugin contract"},
+                      "route": "forward -> loss -> backward -> optimizer.step() through the plugin contract, captured once in a "
+                               "CUDA graph and replayed per batch (GraphedStep; device-side optimizer clock)"},
+           "eager_ms_per_step": round(ms_eager, 5),
            "e2e": {"value": round(world * B * C / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 5),
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
            "gpu_launches_per_step": int(launches // max(steps, 1)), "final_loss": round(float(loss), 6),
+           "gpu_launches": int(launches // max(steps, 1)) * steps,
            "roofline": {"bound": "hbm", "achieved": round(bytes_s, 1), "peak": hbm, "unit": "GB/s",
                         "frac": round(bytes_s / hbm, 4), "traffic": None, "peak_source": src,
                         "alg_bytes_per_step": int(alg_bytes_per_sample(w) * B), "scope": "whole step (SURVEY 8d bytes, no optimizer)"},

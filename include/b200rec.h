@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2R_VERSION 100          /* major*10000 + minor*100 + patch */
+#define B2R_VERSION 101          /* major*10000 + minor*100 + patch */
 
 #define B2R_E_BADARG   (-1)      /* null pointer, d % 4 != 0, negative size ... */
 #define B2R_E_WORKSPACE (-2)     /* workspace too small */
@@ -152,7 +152,14 @@ typedef struct {
     float   lr, beta1, beta2, eps, weight_decay, bc1, bc2;
     int32_t state_ld;   /* row stride (floats) of the m / v arrays in the row-sparse kernels; 0 = d.  2*d lets a table
                            keep m and v interleaved per row ([n_rows][2][d]): one 2*4d-byte burst instead of two */
+    const float* clock; /* NULL: bc1 / bc2 above are used.  Else a DEVICE array float[4] kept by b2r_optim_tick:
+                           [0] = step count t, [1] = lr / (1 - beta1^t), [2] = 1 / sqrt(1 - beta2^t); the kernels read the
+                           Adam step size and bias correction from there, so an enqueued / graph-captured optimizer
+                           launch needs no per-step host parameters */
 } b2r_optim;
+
+/* advance a device-side optimizer clock by one step (see b2r_optim.clock); one thread, double precision */
+B2R_API int b2r_optim_tick(float* clock, float lr, float beta1, float beta2, b2r_stream_t stream);
 
 /* Segment reduce over a plan built on the concatenation of up to two sources' ids
  * (positions [0, s0.n) belong to s0, [s0.n, s0.n + s1.n) to s1; s1 may be NULL).

@@ -642,8 +642,10 @@ template <int LPR, int MODE>
 __global__ void __launch_bounds__(kBT)
 k_apply_sorted(const __grid_constant__ ApplyJob a, const __grid_constant__ ApplyJob b, const __grid_constant__ OptK opt) {
     __shared__ float4 part[kBT / LPR][LPR];    // only touched when the batch has rows with >= kLong contributions
-    if ((int)blockIdx.x < a.grid) apply_job<LPR, MODE>(a, opt, (int)blockIdx.x, part);
-    else apply_job<LPR, MODE>(b, opt, (int)blockIdx.x - a.grid, part);
+    OptK o = opt;
+    optk_use_clock(o);
+    if ((int)blockIdx.x < a.grid) apply_job<LPR, MODE>(a, o, (int)blockIdx.x, part);
+    else apply_job<LPR, MODE>(b, o, (int)blockIdx.x - a.grid, part);
 }
 
 struct BucketGeom {

@@ -107,7 +107,16 @@ struct OptK {
     int kind;          // 0 SGD, 1 Adam, 2 Adagrad
     int state_ld;
     float lr, beta1, beta2, eps, wd, omb1, omb2, step, isb2;
+    const float* clock;   // device-side optimizer clock (b2r_optim.clock): step / isb2 are read from it when set
 };
+
+// kernels call this once on their private copy: Adam's step size and bias correction come from the device clock
+__device__ __forceinline__ void optk_use_clock(OptK& o) {
+    if (o.clock != nullptr) {
+        o.step = __ldg(o.clock + 1);
+        o.isb2 = __ldg(o.clock + 2);
+    }
+}
 
 static inline OptK make_optk(const b2r_optim& o) {
     OptK k;
@@ -122,6 +131,7 @@ static inline OptK make_optk(const b2r_optim& o) {
     k.omb2 = (float)(1.0 - (double)o.beta2);
     k.step = (o.kind == 1 && o.bc1 != 0.f) ? (float)((double)o.lr / (double)o.bc1) : o.lr;
     k.isb2 = (o.kind == 1 && o.bc2 > 0.f) ? (float)(1.0 / sqrt((double)o.bc2)) : 1.f;
+    k.clock = (o.kind == 1) ? o.clock : nullptr;
     return k;
 }
 

@@ -61,6 +61,7 @@ k_segment_apply(const uint32_t* __restrict__ sorted_key, const uint32_t* __restr
                 Src s0, Src s1, int64_t* __restrict__ uniq_rows, float* __restrict__ grad_rows,
                 float* __restrict__ dense, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V,
                 OptK opt) {
+    optk_use_clock(opt);
     constexpr int D = LPR * 4;
     constexpr int GPC = 256 / LPR;
     const int sub = threadIdx.x % LPR;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256)
 k_segment_optim(const uint32_t* __restrict__ sorted_key, const uint32_t* __restrict__ sorted_pos,
                 const int32_t* __restrict__ seg_start, const int32_t* __restrict__ n_uniq, int n, int64_t n_rows,
                 Src s0, Src s1, float* __restrict__ W, float* __restrict__ M, float* __restrict__ V, OptK opt) {
+    optk_use_clock(opt);
     static_assert(RPI < LPR, "segment bounds are loaded one per lane");
     constexpr int D = LPR * 4;
     constexpr int GPC = 256 / LPR;
@@ -192,6 +194,7 @@ k_segment_apply_generic(const uint32_t* __restrict__ sorted_key, const uint32_t*
                         int64_t n_rows, int d, Src s0, Src s1, int64_t* __restrict__ uniq_rows, float* __restrict__ grad_rows,
                         float* __restrict__ dense, float* __restrict__ W, float* __restrict__ M,
                         float* __restrict__ V, OptK opt) {
+    optk_use_clock(opt);
     const int lane = threadIdx.x & 31;
     const int nu = *n_uniq;
     const int d4 = d >> 2;
@@ -253,6 +256,7 @@ k_scatter_add_atomic(const int64_t* __restrict__ ids, int64_t n_rows, Src s, int
 __global__ void __launch_bounds__(256)
 k_dense_optim(float* __restrict__ W, const float* __restrict__ G, float* __restrict__ M, float* __restrict__ V,
               int64_t numel, OptK opt) {
+    optk_use_clock(opt);
     const int64_t n4 = numel >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 w = ld4(W + i * 4), m, v;
@@ -399,5 +403,24 @@ extern "C" int b2r_dense_optim(float* W, const float* grad, float* m, float* v, 
     const int64_t cap = (int64_t)sm_count() * 16;
     k_dense_optim<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(W, grad, m, v, numel, make_optk(*opt));
     B2R_LAUNCH_OK("k_dense_optim");
+    return 0;
+}
+
+// ---- device-side optimizer clock (b2r_optim.clock) ---------------------------------------------------------------------
+namespace b2r {
+__global__ void k_optim_tick(float* __restrict__ clock, float lr, float beta1, float beta2) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double t = (double)clock[0] + 1.0;
+        clock[0] = (float)t;
+        clock[1] = (float)((double)lr / (1.0 - pow((double)beta1, t)));       // lr / bias_correction1
+        clock[2] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, t)));          // 1 / sqrt(bias_correction2)
+    }
+}
+}  // namespace b2r
+
+extern "C" int b2r_optim_tick(float* clock, float lr, float beta1, float beta2, b2r_stream_t stream) {
+    B2R_REQUIRE(clock, B2R_E_BADARG, "b2r_optim_tick: null pointer");
+    b2r::k_optim_tick<<<1, 32, 0, as_stream(stream)>>>(clock, lr, beta1, beta2);
+    B2R_LAUNCH_OK("k_optim_tick");
     return 0;
 }

@@ -25,7 +25,7 @@ class Optim(C.Structure):
     """b2r_optim (include/b200rec.h)"""
     _fields_ = [("kind", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float),
                 ("eps", C.c_float), ("weight_decay", C.c_float), ("bc1", C.c_float), ("bc2", C.c_float),
-                ("state_ld", C.c_int32)]
+                ("state_ld", C.c_int32), ("clock", C.c_void_p)]
 
 
 class BprmfTables(C.Structure):
@@ -83,6 +83,7 @@ SIGNATURES = {
                                         C.POINTER(Optim), C.c_void_p]),
     "b2r_scatter_add_atomic": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(GradSource), C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
+    "b2r_optim_tick": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "b2r_dense_optim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.POINTER(Optim), C.c_void_p]),
     "b2r_linear_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,

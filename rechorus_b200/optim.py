@@ -28,7 +28,7 @@ _DEFAULT_EPS = {"SGD": 0.0, "Adam": 1e-8, "Adagrad": 1e-10}
 
 class RowSparseOptimizer:
     def __init__(self, model: torch.nn.Module, name: str = "Adam", lr: float = 1e-3, l2: float = 0.0,
-                 betas=(0.9, 0.999), eps: float | None = None, exact_dense: bool = False):
+                 betas=(0.9, 0.999), eps: float | None = None, exact_dense: bool = False, device_clock: bool = False):
         """exact_dense (Adam only; next-round groundwork, not yet run on a GPU): keep the row-sparse cost but
         reproduce the reference's dense torch.optim.Adam -- every fused table gets a per-row "up to date as of step"
         stamp, rows are advanced through the steps they skipped before a forward reads them (``before_forward``)
@@ -38,6 +38,13 @@ class RowSparseOptimizer:
         if exact_dense and name != "Adam":
             raise ValueError("exact_dense applies to Adam only (row-sparse SGD without weight decay already is exact)")
         self.exact_dense = bool(exact_dense)
+        if exact_dense and device_clock:
+            raise ValueError("exact_dense keeps its bookkeeping on the host: not available with device_clock")
+        # device_clock: the step count and Adam's bias corrections live in a 4-float device array advanced by a one-thread
+        # kernel inside step() (b2r_optim_tick); the update kernels read them from there, so a step enqueued once -- or
+        # captured in a CUDA graph (rechorus_b200.graph.GraphedStep) -- stays correct when replayed
+        self.clock = None
+        self._want_clock = bool(device_clock)
         self.name, self.kind = name, _KIND[name]
         self.lr, self.l2, self.betas = float(lr), float(l2), (float(betas[0]), float(betas[1]))
         self.eps = _DEFAULT_EPS[name] if eps is None else float(eps)
@@ -97,11 +104,32 @@ class RowSparseOptimizer:
 
     def _opt(self, wd: float, state_ld: int = 0) -> _lib.Optim:
         b1, b2 = self.betas
-        return _lib.Optim(self.kind, self.lr, b1, b2, self.eps, wd, 1.0 - b1 ** self.t, 1.0 - b2 ** self.t, state_ld)
+        t = max(self.t, 1)
+        clock = self.clock.data_ptr() if self.clock is not None else None
+        return _lib.Optim(self.kind, self.lr, b1, b2, self.eps, wd, 1.0 - b1 ** t, 1.0 - b2 ** t, state_ld, clock)
+
+    def _tick(self) -> None:
+        """one optimizer step begins: host counter, and the device clock when there is one"""
+        self.t += 1
+        if self._want_clock:
+            if self.clock is None:
+                dev = next(e["p"].device for e in self._entries)
+                self.clock = torch.zeros(4, dtype=torch.float32, device=dev)
+                if self.t > 1:                                   # resume from a host-counted history
+                    self.clock[0] = float(self.t - 1)
+            from . import lib as L_
+            L_.check(L_.load().b2r_optim_tick(self.clock.data_ptr(), self.lr, self.betas[0], self.betas[1],
+                                              torch.cuda.current_stream().cuda_stream), "b2r_optim_tick")
+
+    def sync_clock(self) -> int:
+        """after graph replays the host counter is stale: read the step count back from the device clock"""
+        if self.clock is not None:
+            self.t = int(round(float(self.clock[0].item())))
+        return self.t
 
     @torch.no_grad()
     def step(self) -> None:
-        self.t += 1
+        self._tick()
         for e in self._entries:
             p = e["p"]
             pend = getattr(p, "_b2r_pending", None)
@@ -144,7 +172,7 @@ class RowSparseOptimizer:
 
     def advance(self) -> int:
         """count one optimizer step taken outside ``step()`` (the C-side whole-step entry points)"""
-        self.t += 1
+        self._tick()
         return self.t
 
     # -- checkpointing (the reference saves no optimizer state; kept for completeness) -------------------

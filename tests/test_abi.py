@@ -34,8 +34,8 @@ def test_binding_table_matches_header(built_lib):
     from rechorus_b200 import lib as L
     assert sorted(L.SIGNATURES) == _declared()
     handle = L.load()
-    assert handle.b2r_version() == 100
-    assert ctypes.sizeof(L.GradSource) == 40 and ctypes.sizeof(L.Optim) == 36
+    assert handle.b2r_version() == 101
+    assert ctypes.sizeof(L.GradSource) == 40 and ctypes.sizeof(L.Optim) == 48      # b2r_optim: 9 x 4 bytes, pad, clock pointer
 
 
 def test_bad_arguments_are_rejected_without_a_gpu(built_lib):

@@ -1,0 +1,69 @@
+"""GPU: a whole contract-route training step captured in a CUDA graph (rechorus_b200.graph.GraphedStep) must train exactly
+like the same steps launched eagerly: the device-side optimizer clock (b2r_optim_tick) replaces the per-step host
+parameters (Adam's bias corrections), everything else is the same kernels in the same order."""
+import argparse
+import types
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(name, flags, device_clock):
+    from rechorus_b200 import plugin
+    from rechorus_b200.optim import RowSparseOptimizer
+    cls = getattr(plugin, name)
+    p = cls.parse_model_args(argparse.ArgumentParser())
+    a = p.parse_args(flags + ["--table_mode", "fused"])
+    a.device, a.model_path = torch.device("cuda", 0), "/tmp/_b2r_graph.pt"
+    torch.manual_seed(3)
+    m = cls(a, types.SimpleNamespace(n_users=200, n_items=300)).to(a.device)
+    with torch.no_grad():
+        for q in m.parameters():
+            q.mul_(10.0)
+    m.optimizer = RowSparseOptimizer(m, "Adam", lr=1e-2, l2=1e-5, eps=1e-3, device_clock=device_clock)
+    m.train()
+    return m
+
+
+def _feeds(name, n, B=64, C=6, L=9):
+    g = torch.Generator().manual_seed(8)
+    out = []
+    for _ in range(n):
+        f = {"user_id": torch.randint(1, 200, (B,), generator=g).cuda(), "item_id": torch.randint(1, 300, (B, C), generator=g).cuda(),
+             "batch_size": B, "phase": "train"}
+        if name == "SASRec":
+            lengths = torch.randint(1, L + 1, (B,), generator=g)
+            lengths[0] = L
+            f["history_items"] = (torch.randint(1, 300, (B, L), generator=g) * (torch.arange(L).view(1, L) < lengths.view(B, 1))).cuda()
+            f["lengths"] = lengths.cuda()
+        out.append(f)
+    return out
+
+
+@pytest.mark.parametrize("name,flags", [("BPRMF", ["--emb_size", "64"]),
+                                        ("NeuMF", ["--emb_size", "32", "--layers", "[32, 16]"]),
+                                        ("SASRec", ["--emb_size", "32", "--num_layers", "2", "--num_heads", "2", "--history_max", "9"])])
+def test_graphed_steps_equal_eager_steps(name, flags):
+    from rechorus_b200 import ops
+    from rechorus_b200.graph import GraphedStep
+    feeds = _feeds(name, 7)
+    eager = _build(name, flags, device_clock=False)
+    graphed = _build(name, flags, device_clock=True)
+    step = GraphedStep(graphed, feeds[0], warmup=2)          # 2 eager warm-up steps on feeds[0], then the capture
+    losses_e = []
+    for f in [feeds[0], feeds[0]] + feeds[1:]:               # the same sequence of batches, eagerly
+        eager.optimizer.zero_grad()
+        ls = eager.loss(eager(f))
+        ls.backward()
+        eager.optimizer.step()
+        losses_e.append(float(ls))
+    losses_g = [float(step(f)) for f in feeds[1:]]
+    torch.cuda.synchronize()
+    assert graphed.optimizer.sync_clock() == eager.optimizer.t == 8
+    for a, b in zip(losses_g, losses_e[2:]):
+        assert abs(a - b) <= 1e-6, (losses_g, losses_e)
+    for (k, pa), (_, pb) in zip(graphed.named_parameters(), eager.named_parameters()):
+        assert (pa - pb).abs().max() <= 1e-6, k
+    ops.check_ids()
