@@ -569,7 +569,7 @@ def run_model_steps(wname, args, rank, world, local_rank, sampler, steps_cap):
         loss = model.loss(model(f))
         loss.backward()
         model.optimizer.step()
-        return loss
+        return loss.detach()        # (a kept non-detached loss would pin this step's autograd graph: see GraphedStep)
 
     launches0 = lib.b2r_launch_count()
     ms_eager, loss, win = timed_loop(dist, step, steps, warmup)
@@ -577,12 +577,27 @@ def run_model_steps(wname, args, rank, world, local_rank, sampler, steps_cap):
     sampler.window(*win)
     # the same step captured once in a CUDA graph and replayed (rechorus_b200.graph.GraphedStep): one host launch per step
     from rechorus_b200.graph import GraphedStep
-    gstep = GraphedStep(model, feeds[0], warmup=2)
-    ms, loss, win = timed_loop(dist, lambda k: gstep(feeds[k % len(feeds)]), steps, warmup)
-    loss = loss.clone()
-    sampler.window(*win)
+    graph_error = None
+    try:
+        gstep = GraphedStep(model, feeds[0], warmup=2)
+        ms, loss, win = timed_loop(dist, lambda k: gstep(feeds[k % len(feeds)]), steps, warmup)
+        loss = loss.clone()
+        sampler.window(*win)
+    except Exception as e:                             # report the eagerly launched step rather than no line at all
+        graph_error = repr(e)[:200]
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        gstep, ms = None, ms_eager
 
     def step_e2e(k):
+        if gstep is None:                              # eager fallback: H2D of the pinned batch, then the same step
+            pf = pinned[k % len(pinned)]
+            f = {kk: (v.to(device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for kk, v in pf.items()}
+            model.optimizer.zero_grad()
+            ls = model.loss(model(f))
+            ls.backward()
+            model.optimizer.step()
+            return float(ls.detach())
         ls = gstep(pinned[k % len(pinned)])            # H2D of the batch into the graph's static buffers, replay
         return float(ls)                               # the runner reads every step's loss (BaseRunner.py:207)
 
@@ -596,9 +611,10 @@ def run_model_steps(wname, args, rank, world, local_rank, sampler, steps_cap):
     h2d = sum(v.numel() * 8 for v in host[0].values())
     out = {"value": round(value, 1), "unit": UNIT, "ms_per_step": round(ms, 5), "steps": steps, "warmup": warmup,
            "config": {"workload": wname + ": " + w["desc"], "optimizer": "Adam lr=1e-3 (tables row-sparse/lazy, dense parameters exact)",
-                      "route": "forward -> loss -> backward -> optimizer.step() through the plugin contract, captured once in a "
-                               "CUDA graph and replayed per batch (GraphedStep; device-side optimizer clock)"},
-           "eager_ms_per_step": round(ms_eager, 5),
+                      "route": ("forward -> loss -> backward -> optimizer.step() through the plugin contract, captured once in a "
+                                "CUDA graph and replayed per batch (GraphedStep; device-side optimizer clock)") if graph_error is None
+                               else "forward -> loss -> backward -> optimizer.step() through the plugin contract, launched eagerly"},
+           "eager_ms_per_step": round(ms_eager, 5), "graph_error": graph_error,
            "e2e": {"value": round(world * B * C / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 5),
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
            "gpu_launches_per_step": int(launches // max(steps, 1)), "final_loss": round(float(loss), 6),

@@ -158,8 +158,10 @@ typedef struct {
                            launch needs no per-step host parameters */
 } b2r_optim;
 
-/* advance a device-side optimizer clock by one step (see b2r_optim.clock); one thread, double precision */
-B2R_API int b2r_optim_tick(float* clock, float lr, float beta1, float beta2, b2r_stream_t stream);
+/* advance a device-side optimizer clock by one step (see b2r_optim.clock); one thread, double precision.  The betas are
+ * doubles (torch computes 1 - beta ** t from the python floats); the bias corrections are rounded to float before use,
+ * as the host-parameter route (bc1 / bc2 above) does, so both routes take bit-identical step sizes */
+B2R_API int b2r_optim_tick(float* clock, float lr, double beta1, double beta2, b2r_stream_t stream);
 
 /* Segment reduce over a plan built on the concatenation of up to two sources' ids
  * (positions [0, s0.n) belong to s0, [s0.n, s0.n + s1.n) to s1; s1 may be NULL).

@@ -408,17 +408,21 @@ extern "C" int b2r_dense_optim(float* W, const float* grad, float* m, float* v, 
 
 // ---- device-side optimizer clock (b2r_optim.clock) ---------------------------------------------------------------------
 namespace b2r {
-__global__ void k_optim_tick(float* __restrict__ clock, float lr, float beta1, float beta2) {
+// the betas arrive as doubles and the bias corrections are rounded to float before use, exactly as the host route does
+// (python computes 1 - beta ** t in double, b2r_optim carries it as float, make_optk divides in double): a replayed step
+// uses the same step size as the eagerly launched one
+__global__ void k_optim_tick(float* __restrict__ clock, float lr, double beta1, double beta2) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const double t = (double)clock[0] + 1.0;
+        const float bc1 = (float)(1.0 - pow(beta1, t)), bc2 = (float)(1.0 - pow(beta2, t));
         clock[0] = (float)t;
-        clock[1] = (float)((double)lr / (1.0 - pow((double)beta1, t)));       // lr / bias_correction1
-        clock[2] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, t)));          // 1 / sqrt(bias_correction2)
+        clock[1] = (float)((double)lr / (double)bc1);                          // lr / bias_correction1
+        clock[2] = (float)(1.0 / sqrt((double)bc2));                           // 1 / sqrt(bias_correction2)
     }
 }
 }  // namespace b2r
 
-extern "C" int b2r_optim_tick(float* clock, float lr, float beta1, float beta2, b2r_stream_t stream) {
+extern "C" int b2r_optim_tick(float* clock, float lr, double beta1, double beta2, b2r_stream_t stream) {
     B2R_REQUIRE(clock, B2R_E_BADARG, "b2r_optim_tick: null pointer");
     b2r::k_optim_tick<<<1, 32, 0, as_stream(stream)>>>(clock, lr, beta1, beta2);
     B2R_LAUNCH_OK("k_optim_tick");

@@ -8,6 +8,12 @@ synchronisation, scratch memory comes from torch's caching allocator (graph-priv
 optimizer's per-step scalars (Adam's bias corrections) live on the device (``RowSparseOptimizer(device_clock=True)``,
 ``b2r_optim_tick``) instead of in kernel parameters.  Batches are copied into static device buffers before each replay;
 shapes are fixed at capture time (a ragged last batch goes through the eager path).
+
+One precondition comes from autograd, not from this package: a parameter's AccumulateGrad node is bound to the stream
+that was current when the node was created and lives as long as any autograd graph that reaches it.  If the caller still
+holds the (non-detached) loss of an eager step that ran on the legacy default stream, the capture's backward would make
+the legacy stream wait on the capturing stream (cudaErrorStreamCaptureImplicit).  Drop or ``detach()`` such losses before
+building a GraphedStep; the constructor turns that CUDA error into a message that says so.
 """
 from __future__ import annotations
 
@@ -35,8 +41,15 @@ class GraphedStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
-            self.loss = self._step()
+        try:
+            with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
+                self.loss = self._step()
+        except Exception as e:
+            if "legacy stream" in repr(e) or "previous error during capture" in repr(e):
+                raise RuntimeError("GraphedStep: the capture was invalidated -- most likely an autograd graph of an earlier eager "
+                                   "step on the default stream is still alive (a loss tensor kept without .detach()); see the "
+                                   "module docstring") from e
+            raise
         self.steps_outside_graph = max(1, warmup) + 1      # the capture itself does not execute the step
 
     def _step(self) -> torch.Tensor:

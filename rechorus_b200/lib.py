@@ -83,7 +83,7 @@ SIGNATURES = {
                                         C.POINTER(Optim), C.c_void_p]),
     "b2r_scatter_add_atomic": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(GradSource), C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
-    "b2r_optim_tick": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "b2r_optim_tick": (C.c_int, [C.c_void_p, C.c_float, C.c_double, C.c_double, C.c_void_p]),
     "b2r_dense_optim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.POINTER(Optim), C.c_void_p]),
     "b2r_linear_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
