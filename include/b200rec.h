@@ -306,6 +306,17 @@ B2R_API int b2r_attention_fwd_live(const float* q, const float* k, const float* 
 B2R_API int b2r_attention_bwd_live(const float* q, const float* k, const float* v, int ld, const int64_t* live,
                                    const float* dctx, float* dq, float* dk, float* dv, int ldg, int B, int L, int d, int H,
                                    b2r_stream_t stream);
+/* The same function with the per-(row, head) state in registers (csrc/attention_rt.cu): one lane owns one query row (forward,
+ * dQ) or one key row (dK, dV) of one head, the other operand arrives as broadcast shared-memory loads.  The forward also
+ * writes lse [B, L, H]: log2 of the softmax denominator plus the running max (base-2 domain); the backward recomputes the
+ * probabilities from it and takes the forward's output ctx for the softmax-Jacobian row term dO_i . O_i.
+ * Covers d/H in {8, 16, 32}, L <= 128, d and ld multiples of 4, 16-byte aligned pointers; anything else returns
+ * B2R_E_UNSUPPORTED (callers fall back to b2r_attention_*_live).  Same dead-row contract. */
+B2R_API int b2r_attention_fwd_rt(const float* q, const float* k, const float* v, int ld, const int64_t* live, float* ctx,
+                                 float* lse, int B, int L, int d, int H, b2r_stream_t stream);
+B2R_API int b2r_attention_bwd_rt(const float* q, const float* k, const float* v, int ld, const int64_t* live,
+                                 const float* ctx, const float* lse, const float* dctx, float* dq, float* dk, float* dv,
+                                 int ldg, int B, int L, int d, int H, b2r_stream_t stream);
 /* Attention for ONE query per
  * sequence -- the query at position t* = clamp(lengths[b]-1, 0, L-1), the only position of SASRec's last block whose
  * output is used (models/sequential/SASRec.py:74-81) -- against keys/values 0..t* (the causal row of

@@ -16,6 +16,7 @@
 // reads the accumulator back with tcgen05.ld (32 lanes x 16 columns per instruction), adds the bias, applies ReLU and
 // writes Y.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace b2r {
 
@@ -104,7 +105,7 @@ __device__ __forceinline__ void tc_store_split(char* hi_base, char* lo_base, int
 template <int KS>
 __global__ void __launch_bounds__(TC_THREADS)
 k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ amask, const float* __restrict__ W,
-                const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int N, int relu, int tmem_cols) {
+                const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int N, int relu, int tmem_cols, int nprod) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar;
     __shared__ uint32_t tmem_base_sh;
@@ -141,50 +142,55 @@ k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ 
 
     uint32_t parity = 0;
     const int ntiles = (M + TC_M - 1) / TC_M;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // Software pipeline over this CTA's tiles: the 8*KS 128-bit loads of the NEXT tile are issued right after this tile's
+    // MMAs and stay in flight through the MMA wait and the epilogue; shared memory and the TMEM accumulator are single
+    // buffers (the mbarrier wait orders "MMAs done" before both are reused), several CTAs per SM cover the rest.
+    float4 v[8 * KS];
+#define TC_ISSUE_LOADS(TILE)                                                                         \
+    do {                                                                                             \
+        const int m0_ = (TILE) * TC_M;                                                               \
+        _Pragma("unroll") for (int i = 0; i < 8 * KS; ++i) {                                         \
+            const int e = i * TC_THREADS + tid;                                                      \
+            const int c = e % 8, s_ = (e / 8) % KS, r = e / (8 * KS);                                \
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);                                                  \
+            if (m0_ + r < M) {                                                                       \
+                const size_t g = (size_t)(m0_ + r) * ldx + s_ * 32 + c * 4;                          \
+                v[i] = ld_row4(X + g);                                                               \
+                if (amask != nullptr) {      /* ReLU backward: keep dY where the saved output > 0 */ \
+                    const float4 mk = ld_row4(amask + g);                                            \
+                    v[i].x = mk.x > 0.f ? v[i].x : 0.f;                                              \
+                    v[i].y = mk.y > 0.f ? v[i].y : 0.f;                                              \
+                    v[i].z = mk.z > 0.f ? v[i].z : 0.f;                                              \
+                    v[i].w = mk.w > 0.f ? v[i].w : 0.f;                                              \
+                }                                                                                    \
+            }                                                                                        \
+        }                                                                                            \
+    } while (0)
+    int tile = blockIdx.x;
+    if (tile < ntiles) TC_ISSUE_LOADS(tile);
+    for (; tile < ntiles; tile += gridDim.x) {
         const int m0 = tile * TC_M;
-        // X tile -> A_hi / A_lo: all 8*KS 128-bit loads of a thread are issued before the first use
-        {
-            float4 v[8 * KS];
 #pragma unroll
-            for (int i = 0; i < 8 * KS; ++i) {
-                const int e = i * TC_THREADS + tid;
-                const int c = e % 8, s = (e / 8) % KS, r = e / (8 * KS);
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m0 + r < M) {
-                    const size_t g = (size_t)(m0 + r) * ldx + s * 32 + c * 4;
-                    v[i] = ld_row4(X + g);
-                    if (amask != nullptr) {                          // ReLU backward: keep dY where the saved output > 0
-                        const float4 mk = ld_row4(amask + g);
-                        v[i].x = mk.x > 0.f ? v[i].x : 0.f;
-                        v[i].y = mk.y > 0.f ? v[i].y : 0.f;
-                        v[i].z = mk.z > 0.f ? v[i].z : 0.f;
-                        v[i].w = mk.w > 0.f ? v[i].w : 0.f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8 * KS; ++i) {
-                const int e = i * TC_THREADS + tid;
-                const int c = e % 8, s = (e / 8) % KS, r = e / (8 * KS);
-                tc_store_split(A_hi + s * a_slab, A_lo + s * a_slab, r, c, v[i]);
-            }
+        for (int i = 0; i < 8 * KS; ++i) {
+            const int e = i * TC_THREADS + tid;
+            const int c = e % 8, s_ = (e / 8) % KS, r = e / (8 * KS);
+            tc_store_split(A_hi + s_ * a_slab, A_lo + s_ * a_slab, r, c, v[i]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async proxy (UMMA)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        __syncthreads();                  // also: every thread's tcgen05.ld of the previous tile has completed (wait::ld)
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t acc = 0;
 #pragma unroll 1
-            for (int prod = 0; prod < 4; ++prod) {
-                const char* Ab = (prod < 2) ? A_hi : A_lo;              // hi*hi, hi*lo, lo*hi, lo*lo
+            for (int prod = 0; prod < nprod; ++prod) {
+                const char* Ab = (prod < 2) ? A_hi : A_lo;              // hi*hi, hi*lo, lo*hi [, lo*lo]
                 const char* Bb = (prod & 1) ? B_lo : B_hi;
-                for (int s = 0; s < KS; ++s) {
+                for (int s_ = 0; s_ < KS; ++s_) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {                       // 4 MMAs of K = 8 floats (32 bytes) per slab
-                        const uint64_t ad = tc_desc(tc_smem_u32(Ab + s * a_slab) + k * 32);
-                        const uint64_t bd = tc_desc(tc_smem_u32(Bb + s * b_slab) + k * 32);
+                        const uint64_t ad = tc_desc(tc_smem_u32(Ab + s_ * a_slab) + k * 32);
+                        const uint64_t bd = tc_desc(tc_smem_u32(Bb + s_ * b_slab) + k * 32);
                         tc_mma_tf32(tmem, ad, bd, idesc, acc);
                         acc = 1;
                     }
@@ -192,29 +198,31 @@ k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ 
             }
             tc_commit(&mma_bar);
         }
+        if (tile + (int)gridDim.x < ntiles) TC_ISSUE_LOADS(tile + (int)gridDim.x);
         tc_mbar_wait(&mma_bar, parity);
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // epilogue: thread = row (TMEM lane), 16 columns per tcgen05.ld
         const int row = m0 + warp * 32 + lane;
         for (int c0 = 0; c0 < N; c0 += 16) {
-            float v[16];
-            tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            float y16[16];
+            tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, y16);
             if (row < M) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float y = v[i] + (bias != nullptr ? bias[c0 + i] : 0.f);
+                    float y = y16[i] + (bias != nullptr ? bias[c0 + i] : 0.f);
                     if (relu) y = fmaxf(y, 0.f);
-                    v[i] = y;
+                    y16[i] = y;
                 }
                 float* dst = Y + (size_t)row * ldy + c0;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(y16[i], y16[i + 1], y16[i + 2], y16[i + 3]);
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                                 // TMEM and the A buffers are free again
     }
+#undef TC_ISSUE_LOADS
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
     }
@@ -243,14 +251,22 @@ extern "C" int b2r_linear_tc(const float* X, int ldx, const float* x_mask, const
     int cols = 32;
     while (cols < N) cols <<= 1;
     const int ntiles = (int)((M + TC_M - 1) / TC_M);
-    const int per_sm = (smem <= 100 * 1024) ? 2 : 1;
+    // CTAs per SM: by shared memory (227 KB) and TMEM columns (512), at most 4; B2R_TC_CTAS overrides for A/B
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 512 / cols) per_sm = 512 / cols;
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    static const int env_ctas = getenv("B2R_TC_CTAS") ? atoi(getenv("B2R_TC_CTAS")) : 0;
+    if (env_ctas > 0 && env_ctas < per_sm) per_sm = env_ctas;
+    // 3 products (hi*hi + hi*lo + lo*hi, |err| <= 2^-21 of the fp32 dot) unless B2R_TC_PRODS=4 adds lo*lo
+    static const int nprod = (getenv("B2R_TC_PRODS") && atoi(getenv("B2R_TC_PRODS")) == 4) ? 4 : 3;
     int grid = sm_count() * per_sm;
     if (grid > ntiles) grid = ntiles;
 #define B2R_TC(KSV)                                                                                    \
     do {                                                                                               \
         B2R_CUDA_OK(cudaFuncSetAttribute(k_linear_fwd_tc<KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_linear_fwd_tc<KSV><<<grid, TC_THREADS, smem, as_stream(stream)>>>(X, ldx, x_mask, W, bias, Y, ldy, (int)M, N, relu, \
-                                                                            cols);                     \
+                                                                            cols, nprod);              \
     } while (0)
     if (KS == 1) B2R_TC(1); else if (KS == 2) B2R_TC(2); else if (KS == 3) B2R_TC(3); else B2R_TC(4);
 #undef B2R_TC

@@ -806,17 +806,19 @@ def linear_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], r
     return y
 
 
-def linear_fwd_tc(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
-    """same as linear_fwd on the tcgen05 tensor cores (TF32 hi/lo split, fp32-class accuracy); raises for shapes
-    outside the kernel's class"""
+def linear_fwd_tc(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], relu: bool, strict: bool = True):
+    """same as linear_fwd on the tcgen05 tensor cores (TF32 hi/lo split, fp32-class accuracy); for shapes outside the
+    kernel's class it raises (strict) or returns None"""
     _need_cuda(x, W)
     M, ldx = _rows_ld(x)
     N, K = W.shape
     W = _f32c(W, "W")
     y = torch.empty((M, N), dtype=torch.float32, device=x.device)
     L = _lib.load()
-    _lib.check(L.b2r_linear_fwd_tc(_p(x), ldx, _p(W), _p(bias), _p(y), N, M, N, K, 1 if relu else 0, _stream()),
-               "b2r_linear_fwd_tc")
+    rc = L.b2r_linear_fwd_tc(_p(x), ldx, _p(W), _p(bias), _p(y), N, M, N, K, 1 if relu else 0, _stream())
+    if rc == -3 and not strict:
+        return None
+    _lib.check(rc, "b2r_linear_fwd_tc")
     return y
 
 
@@ -834,8 +836,17 @@ def linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, y_relu: Optio
         lddy = N
     if need_dx:
         dx = torch.empty((M, K), dtype=torch.float32, device=dy.device)
-        _lib.check(L.b2r_linear_bwd_input(_p(dy), lddy, _p(y_relu), _p(W), _p(dx), K, M, N, K, _stream()),
-                   "b2r_linear_bwd_input")
+        done = False
+        if _TC_LINEAR and M >= 4096 and N % 32 == 0 and N <= 128 and K % 16 == 0 and K <= 256 and lddy % 4 == 0:
+            # dX = (dY o mask) W = (dY o mask) (W^T)^T on the tcgen05 kernel: the transposed weight (N*K floats) is a copy
+            Wt = W.t().contiguous()
+            rc = L.b2r_linear_tc(_p(dy), lddy, _p(y_relu), _p(Wt), None, _p(dx), K, M, K, N, 0, _stream())
+            done = rc == 0
+            if rc not in (0, -3):
+                _lib.check(rc, "b2r_linear_tc")
+        if not done:
+            _lib.check(L.b2r_linear_bwd_input(_p(dy), lddy, _p(y_relu), _p(W), _p(dx), K, M, N, K, _stream()),
+                       "b2r_linear_bwd_input")
     if need_dw or need_db:
         dW = torch.empty((N, K), dtype=torch.float32, device=dy.device)
         db = torch.empty((N,), dtype=torch.float32, device=dy.device) if need_db else None
@@ -872,9 +883,11 @@ class _Linear(torch.autograd.Function):
         if x2.stride(1) != 1:
             x2 = x2.contiguous()
         N, K = W.shape
-        if _TC_LINEAR and K % 32 == 0 and K <= 128 and N % 16 == 0 and N <= 256:
-            y = linear_fwd_tc(x2, W, bias, relu)          # tcgen05 TF32-split forward (opt-in, B2R_TC_LINEAR=1)
+        if _TC_LINEAR and x2.shape[0] >= 4096 and K % 32 == 0 and K <= 128 and N % 16 == 0 and N <= 256:
+            y = linear_fwd_tc(x2, W, bias, relu, strict=False)          # tcgen05 TF32-split forward
         else:
+            y = None
+        if y is None:
             y = linear_fwd(x2, W, bias, relu)
         ctx.save_for_backward(x2, W, y if relu else None)
         ctx.has_bias, ctx.shape = bias is not None, shape
@@ -935,6 +948,10 @@ def add_layernorm(x, res, gamma, beta, eps=1e-5):
     return _AddLayerNorm.apply(x, res, gamma, beta, eps)
 
 
+# B2R_ATTN=v1: the first (shared-memory operand) attention kernels for every shape, for A/B
+_ATTN_RT = os.environ.get("B2R_ATTN", "rt") != "v1"
+
+
 class _CausalAttention(torch.autograd.Function):
     """layers.py:52-63 for q,k,v [B, L, d] with H heads (contiguous d/H chunks), causal mask, no W_o.  ``live`` (optional
     int64 [B]): positions >= live[b] are dead rows (nothing downstream reads them): skipped, written as zeros."""
@@ -947,21 +964,35 @@ class _CausalAttention(torch.autograd.Function):
         live = None if live is None else _i64c(live, "live lengths")
         out = torch.empty((B, Ln, d), dtype=torch.float32, device=q.device)
         L = _lib.load()
-        _lib.check(L.b2r_attention_fwd_live(_p(q), _p(k), _p(v), d, _p(live), _p(out), B, Ln, d, H, _stream()),
-                   "b2r_attention_fwd")
-        ctx.save_for_backward(q, k, v, live)
+        lse = None
+        if _ATTN_RT and d % H == 0 and d // H in (8, 16, 32) and Ln <= 128:
+            # register-resident kernels (csrc/attention_rt.cu); the row log-sum-exp is kept for the backward
+            lse = torch.empty((B, Ln, H), dtype=torch.float32, device=q.device)
+            rc = L.b2r_attention_fwd_rt(_p(q), _p(k), _p(v), d, _p(live), _p(out), _p(lse), B, Ln, d, H, _stream())
+            if rc == -3:                                   # B2R_E_UNSUPPORTED: shape / alignment outside the fast path
+                lse = None
+            else:
+                _lib.check(rc, "b2r_attention_fwd_rt")
+        if lse is None:
+            _lib.check(L.b2r_attention_fwd_live(_p(q), _p(k), _p(v), d, _p(live), _p(out), B, Ln, d, H, _stream()),
+                       "b2r_attention_fwd")
+        ctx.save_for_backward(q, k, v, live, out if lse is not None else None, lse)
         ctx.H = H
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, live = ctx.saved_tensors
+        q, k, v, live, out, lse = ctx.saved_tensors
         B, Ln, d = q.shape
         dout = _f32c(dout, "dctx")
         dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
         L = _lib.load()
-        _lib.check(L.b2r_attention_bwd_live(_p(q), _p(k), _p(v), d, _p(live), _p(dout), _p(dq), _p(dk), _p(dv), d, B, Ln, d,
-                                            ctx.H, _stream()), "b2r_attention_bwd")
+        if lse is not None:
+            _lib.check(L.b2r_attention_bwd_rt(_p(q), _p(k), _p(v), d, _p(live), _p(out), _p(lse), _p(dout), _p(dq), _p(dk),
+                                              _p(dv), d, B, Ln, d, ctx.H, _stream()), "b2r_attention_bwd_rt")
+        else:
+            _lib.check(L.b2r_attention_bwd_live(_p(q), _p(k), _p(v), d, _p(live), _p(dout), _p(dq), _p(dk), _p(dv), d, B, Ln,
+                                                d, ctx.H, _stream()), "b2r_attention_bwd")
         return dq, dk, dv, None, None
 
 

@@ -83,7 +83,7 @@ def _ref_attention(q, k, v, H):
 
 
 @pytest.mark.parametrize("B,L,d,H", [(3, 50, 64, 4), (2, 20, 64, 1), (5, 12, 32, 2), (1, 1, 64, 4), (2, 70, 64, 4),
-                                     (2, 33, 128, 8)])
+                                     (2, 33, 128, 8), (3, 50, 64, 2), (2, 128, 32, 4), (2, 31, 64, 8), (2, 32, 48, 3)])
 def test_causal_attention_forward_backward(B, L, d, H):
     from rechorus_b200 import ops
     g = torch.Generator().manual_seed(B * 100 + L)
@@ -100,7 +100,7 @@ def test_causal_attention_forward_backward(B, L, d, H):
     _close(vc.grad, v.grad, 2e-5)
 
 
-@pytest.mark.parametrize("B,L,d,H", [(6, 50, 64, 4), (4, 33, 128, 8), (3, 7, 32, 2)])
+@pytest.mark.parametrize("B,L,d,H", [(6, 50, 64, 4), (4, 33, 128, 8), (3, 7, 32, 2), (5, 100, 64, 2), (4, 50, 64, 1)])
 def test_causal_attention_with_dead_rows_skipped_equals_full_attention_on_the_live_rows(B, L, d, H):
     """live[b] positions matter, the rest is dead work (SASRec reads position len-1 only and the mask is causal): the
     live rows of the output and of dq/dk/dv equal the full computation's when the dead rows receive no upstream gradient;
