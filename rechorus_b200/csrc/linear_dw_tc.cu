@@ -93,25 +93,42 @@ k_linear_dw_tc(const float* __restrict__ dY, int lddy, const float* __restrict__
             char* hi = (isA ? A_hi + s * a_slab : B_hi + s * b_slab);
             char* lo = (isA ? A_lo + s * a_slab : B_lo + s * b_slab);
             const int nf = isA ? N : K;
-            for (int f0 = 0; f0 < nf; f0 += 4) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (live) {
-                    v = ld4(src + f0);
-                    if (msk != nullptr) {                            // ReLU backward: dY counts where the saved output > 0
-                        const float4 mk = ld4(msk + f0);
-                        v.x = mk.x > 0.f ? v.x : 0.f;
-                        v.y = mk.y > 0.f ? v.y : 0.f;
-                        v.z = mk.z > 0.f ? v.z : 0.f;
-                        v.w = mk.w > 0.f ? v.w : 0.f;
+            // 8 x 128-bit loads (32 features) of the lane's batch row in flight before the first use: the loop is bound by
+            // load latency otherwise (one CTA stages only 64 rows per MMA round)
+            for (int f0 = 0; f0 < nf; f0 += 32) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && f0 + 4 * u < nf) v[u] = ld4(src + f0 + 4 * u);
+                }
+                if (msk != nullptr) {                                // ReLU backward: dY counts where the saved output > 0
+                    float4 mk[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        mk[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (live && f0 + 4 * u < nf) mk[u] = ld4(msk + f0 + 4 * u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v[u].x = mk[u].x > 0.f ? v[u].x : 0.f;
+                        v[u].y = mk[u].y > 0.f ? v[u].y : 0.f;
+                        v[u].z = mk[u].z > 0.f ? v[u].z : 0.f;
+                        v[u].w = mk[u].w > 0.f ? v[u].w : 0.f;
                     }
                 }
-                const float* pv = &v.x;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float h = dw_rn_tf32(pv[i]);
-                    const uint32_t off = dw_off(f0 + i, lane);
-                    *reinterpret_cast<float*>(hi + off) = h;
-                    *reinterpret_cast<float*>(lo + off) = dw_rn_tf32(pv[i] - h);
+                for (int u = 0; u < 8; ++u) {
+                    if (f0 + 4 * u < nf) {
+                        const float pv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float h = dw_rn_tf32(pv[i]);
+                            const uint32_t off = dw_off(f0 + 4 * u + i, lane);
+                            *reinterpret_cast<float*>(hi + off) = h;
+                            *reinterpret_cast<float*>(lo + off) = dw_rn_tf32(pv[i] - h);
+                        }
+                    }
                 }
             }
             if (!isA) {                                              // batch rows beyond the range must not count in dbias

@@ -228,6 +228,180 @@ k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pipelined version (K <= 64): the kernel above keeps 8 warps per SM and is bound by the latency of its own loads (ncu:
+// 11 % issue, 12 % warps active, 1.2 TB/s).  Here the X tiles (and the ReLU mask tiles) travel global -> shared memory as
+// cp.async 16-byte copies into a ring that is NST tiles deep, so 64-96 KB per SM are always in flight; the 256 threads
+// split a landed raw tile into the swizzled hi / lo operand tiles, one thread issues the MMAs into one of TWO TMEM
+// accumulators, and the epilogue of tile i-1 (tcgen05.ld, bias, ReLU, stores) runs while the MMAs of tile i execute.
+//   iteration i:  wait(raw tile i landed) ; wait(MMA i-1 done: hi/lo free) ; split ; MMA i -> acc[i&1] ; refill ring with
+//                 tile i+NST ; epilogue i-1 from acc[(i-1)&1]
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TP_THREADS = 256;
+
+__device__ __forceinline__ void tp_cp16(void* sdst, const void* gsrc, bool valid) {
+    const uint32_t sa = tc_smem_u32(sdst);
+    const int nbytes = valid ? 16 : 0;                       // src-size 0: writes zeros, reads nothing
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(nbytes) : "memory");
+}
+
+template <int KS, bool MASK>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+k_linear_tc_pipe(const float* __restrict__ X, int ldx, const float* __restrict__ amask, const float* __restrict__ W,
+                 const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int N, int relu, int acc_cols,
+                 int nprod) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_base_sh;
+    constexpr int K = KS * 32;
+    constexpr int NST = MASK ? 2 : 3;                        // ring depth (a masked tile is two raw tiles)
+    constexpr int CH = TC_M * K / 4;                         // 16-byte chunks per raw tile
+    constexpr int CPT = CH / TP_THREADS;                     // chunks per thread
+    const size_t a_slab = (size_t)TC_M * 128, b_slab = (size_t)N * 128, raw_tile = (size_t)TC_M * K * 4;
+    char* A_hi = reinterpret_cast<char*>(smem_raw) + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
+    char* A_lo = A_hi + KS * a_slab;
+    char* B_hi = A_lo + KS * a_slab;
+    char* B_lo = B_hi + KS * b_slab;
+    char* ring = B_lo + KS * b_slab;                         // NST x (raw X tile [, raw mask tile])
+    const size_t stage_bytes = raw_tile * (MASK ? 2 : 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_sh)),
+                     "r"(2 * acc_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        tc_mbar_init(&mma_bar[0], 1);
+        tc_mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int ntiles = (M + TC_M - 1) / TC_M;
+    // ring prologue: tiles 0 .. NST-1 of this CTA
+    auto issue_tile = [&](int tile, int stage) {
+        char* dst = ring + (size_t)stage * stage_bytes;
+        const int m0 = tile * TC_M;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int e = i * TP_THREADS + tid;
+            const int r = e / (K / 4), c = e % (K / 4);
+            const bool ok = m0 + r < M;
+            const size_t g = (size_t)(ok ? m0 + r : M - 1) * ldx + c * 4;
+            tp_cp16(dst + (size_t)e * 16, X + g, ok);
+            if (MASK) tp_cp16(dst + raw_tile + (size_t)e * 16, amask + g, ok);
+        }
+    };
+#pragma unroll
+    for (int s_ = 0; s_ < NST; ++s_) {
+        const int t = blockIdx.x + s_ * gridDim.x;
+        if (t < ntiles) issue_tile(t, s_);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    // W -> B_hi / B_lo (once per CTA)
+    for (int e = tid; e < N * KS * 8; e += TP_THREADS) {
+        const int c = e % 8, s_ = (e / 8) % KS, n = e / (8 * KS);
+        const float4 v = *reinterpret_cast<const float4*>(W + (size_t)n * K + s_ * 32 + c * 4);
+        tc_store_split(B_hi + s_ * b_slab, B_lo + s_ * b_slab, n, c, v);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_sh;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+    // epilogue of one finished tile: warp w reads TMEM lanes [32 (w & 3), +32) and the 16-column chunks of parity (w >> 2)
+    auto epilogue = [&](int tile, uint32_t acc_base) {
+        const int row = tile * TC_M + (warp & 3) * 32 + lane;
+        for (int c0 = (warp >> 2) * 16; c0 < N; c0 += 32) {
+            float y16[16];
+            tc_ld16(acc_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, y16);
+            if (row < M) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float y = y16[i] + (bias != nullptr ? __ldg(bias + c0 + i) : 0.f);
+                    if (relu) y = fmaxf(y, 0.f);
+                    y16[i] = y;
+                }
+                float* dst = Y + (size_t)row * ldy + c0;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(y16[i], y16[i + 1], y16[i + 2], y16[i + 3]);
+            }
+        }
+    };
+
+    int it = 0, prev_tile = -1;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int stage = it % NST;
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(NST - 1) : "memory");       // this thread's copies of tile `it` landed
+        if (it > 0) tc_mbar_wait(&mma_bar[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 done: hi/lo free
+        __syncthreads();                                                            // everyone's copies landed
+        {
+            const char* raw = ring + (size_t)stage * stage_bytes;
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+                const int e = i * TP_THREADS + tid;
+                const int r = e / (K / 4), c = e % (K / 4);
+                float4 v = *reinterpret_cast<const float4*>(raw + (size_t)e * 16);
+                if (MASK) {
+                    const float4 mk = *reinterpret_cast<const float4*>(raw + raw_tile + (size_t)e * 16);
+                    v.x = mk.x > 0.f ? v.x : 0.f;
+                    v.y = mk.y > 0.f ? v.y : 0.f;
+                    v.z = mk.z > 0.f ? v.z : 0.f;
+                    v.w = mk.w > 0.f ? v.w : 0.f;
+                }
+                const int s_ = c / 8;
+                tc_store_split(A_hi + s_ * a_slab, A_lo + s_ * a_slab, r, c % 8, v);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc_base = tmem + (uint32_t)((it & 1) * acc_cols);
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int prod = 0; prod < nprod; ++prod) {
+                const char* Ab = (prod < 2) ? A_hi : A_lo;
+                const char* Bb = (prod & 1) ? B_lo : B_hi;
+                for (int s_ = 0; s_ < KS; ++s_) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ad = tc_desc(tc_smem_u32(Ab + s_ * a_slab) + k * 32);
+                        const uint64_t bd = tc_desc(tc_smem_u32(Bb + s_ * b_slab) + k * 32);
+                        tc_mma_tf32(acc_base, ad, bd, idesc, acc);
+                        acc = 1;
+                    }
+                }
+            }
+            tc_commit(&mma_bar[it & 1]);
+        }
+        {   // the raw stage just consumed takes tile it + NST
+            const int nt = tile + NST * (int)gridDim.x;
+            if (nt < ntiles) issue_tile(nt, stage);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        if (it > 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            epilogue(prev_tile, tmem + (uint32_t)(((it - 1) & 1) * acc_cols));
+        }
+        prev_tile = tile;
+    }
+    if (it > 0) {
+        tc_mbar_wait(&mma_bar[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        epilogue(prev_tile, tmem + (uint32_t)(((it - 1) & 1) * acc_cols));
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * acc_cols) : "memory");
+    }
+}
+
 }  // namespace b2r
 
 using namespace b2r;
@@ -246,10 +420,33 @@ extern "C" int b2r_linear_tc(const float* X, int ldx, const float* x_mask, const
         return set_error(B2R_E_UNSUPPORTED, "b2r_linear_fwd_tc: shape M=%lld N=%d K=%d ldx=%d ldy=%d outside the kernel's class",
                          (long long)M, N, K, ldx, ldy);
     const int KS = K / 32;
-    const size_t smem = (size_t)2 * KS * TC_M * 128 + (size_t)2 * KS * N * 128 + 1024;
-    if (smem > 200 * 1024) return set_error(B2R_E_UNSUPPORTED, "b2r_linear_fwd_tc: %zu B of shared memory needed", smem);
     int cols = 32;
     while (cols < N) cols <<= 1;
+    static const bool use_pipe = !(getenv("B2R_TC_PIPE") && atoi(getenv("B2R_TC_PIPE")) == 0);
+    static const int nprod = (getenv("B2R_TC_PRODS") && atoi(getenv("B2R_TC_PRODS")) == 4) ? 4 : 3;
+    if (use_pipe && KS <= 2) {
+        const int nst = x_mask ? 2 : 3;
+        const size_t raw_tile = (size_t)TC_M * K * 4;
+        const size_t psmem = (size_t)2 * KS * TC_M * 128 + (size_t)2 * KS * N * 128 + nst * raw_tile * (x_mask ? 2 : 1) + 1024;
+        if (psmem <= 227 * 1024 && 2 * cols <= 512) {
+            const int ntiles = (int)((M + TC_M - 1) / TC_M);
+            int grid = sm_count();
+            if (grid > ntiles) grid = ntiles;
+#define B2R_TP(KSV, MK)                                                                                       \
+    do {                                                                                                      \
+        B2R_CUDA_OK(cudaFuncSetAttribute(k_linear_tc_pipe<KSV, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
+        k_linear_tc_pipe<KSV, MK><<<grid, TP_THREADS, psmem, as_stream(stream)>>>(X, ldx, x_mask, W, bias, Y, ldy, (int)M, N, \
+                                                                                 relu, cols, nprod);         \
+    } while (0)
+            if (KS == 1) { if (x_mask) B2R_TP(1, true); else B2R_TP(1, false); }
+            else         { if (x_mask) B2R_TP(2, true); else B2R_TP(2, false); }
+#undef B2R_TP
+            B2R_LAUNCH_OK("k_linear_tc_pipe");
+            return 0;
+        }
+    }
+    const size_t smem = (size_t)2 * KS * TC_M * 128 + (size_t)2 * KS * N * 128 + 1024;
+    if (smem > 200 * 1024) return set_error(B2R_E_UNSUPPORTED, "b2r_linear_fwd_tc: %zu B of shared memory needed", smem);
     const int ntiles = (int)((M + TC_M - 1) / TC_M);
     // CTAs per SM: by shared memory (227 KB) and TMEM columns (512), at most 4; B2R_TC_CTAS overrides for A/B
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -258,8 +455,7 @@ extern "C" int b2r_linear_tc(const float* X, int ldx, const float* x_mask, const
     if (per_sm < 1) per_sm = 1;
     static const int env_ctas = getenv("B2R_TC_CTAS") ? atoi(getenv("B2R_TC_CTAS")) : 0;
     if (env_ctas > 0 && env_ctas < per_sm) per_sm = env_ctas;
-    // 3 products (hi*hi + hi*lo + lo*hi, |err| <= 2^-21 of the fp32 dot) unless B2R_TC_PRODS=4 adds lo*lo
-    static const int nprod = (getenv("B2R_TC_PRODS") && atoi(getenv("B2R_TC_PRODS")) == 4) ? 4 : 3;
+    // (nprod above: 3 products hi*hi + hi*lo + lo*hi, |err| <= 2^-21 of the fp32 dot, unless B2R_TC_PRODS=4 adds lo*lo)
     int grid = sm_count() * per_sm;
     if (grid > ntiles) grid = ntiles;
 #define B2R_TC(KSV)                                                                                    \

@@ -866,9 +866,10 @@ def linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, y_relu: Optio
     return dx, dW, db
 
 
-# opt-in: run every Linear forward of the dense models on the tcgen05 kernel (verified to fp32-class accuracy in
-# tests/test_gpu_tc.py, currently ~10 % slower than the SGEMM at K = 64 -- DESIGN.md §6); off unless B2R_TC_LINEAR=1
-_TC_LINEAR = os.environ.get("B2R_TC_LINEAR") == "1"
+# Linear forward and dX with a long batch dimension (M >= 4096) run on the tcgen05 kernels (csrc/linear_tc.cu: TF32 hi/lo
+# split, 3 products, fp32-class accuracy checked in tests/test_gpu_tc.py; the pipelined K <= 64 kernel is ~2x the SGEMM at
+# M = 204800, N = K = 64); B2R_TC_LINEAR=0: CUDA-core SGEMM everywhere
+_TC_LINEAR = os.environ.get("B2R_TC_LINEAR", "1") != "0"
 # weight gradients with a long batch reduction run on the tensor cores (csrc/linear_dw_tc.cu); B2R_TC_DW=0: CUDA cores
 _TC_DW = os.environ.get("B2R_TC_DW", "1") != "0"
 

@@ -50,6 +50,20 @@ def main():
         out.append(dict(M=M, K=K, N=N, rel_err_tc=err, rel_err_fma=err2, ms_tc=round(ms_tc, 4), ms_fma=round(ms_cc, 4),
                         GBps_tc=round(gb / ms_tc * 1e3, 1), TFLOPs_tc=round(2 * M * N * K / ms_tc / 1e9, 2)))
         worst = max(worst, err)
+    # masked form (dX of a ReLU layer): Y = (X o (mask > 0)) W^T through b2r_linear_tc
+    from rechorus_b200 import lib as _lib
+    L = _lib.load()
+    for (M, K, N) in [(300, 64, 64), (5000, 32, 48), (4096 * 50, 64, 64), (1111, 128, 64)]:
+        x = torch.randn(M, K).cuda()
+        mk = torch.randn(M, K).cuda()
+        W = torch.randn(N, K).cuda()
+        y = torch.empty(M, N).cuda()
+        _lib.check(L.b2r_linear_tc(x.data_ptr(), K, mk.data_ptr(), W.data_ptr(), None, y.data_ptr(), N, M, N, K, 0,
+                                   torch.cuda.current_stream().cuda_stream), "b2r_linear_tc")
+        ref = (x.double() * (mk > 0)) @ W.double().t()
+        err = float((y.double() - ref).abs().max()) / float(ref.abs().max())
+        out.append(dict(M=M, K=K, N=N, masked=True, rel_err_tc=err))
+        worst = max(worst, err)
     for o in out:
         print(json.dumps(o))
     assert worst <= 2.5e-6, worst   # tensor-core internal accumulation: ~1-2e-6 relative (fp32 FMA path: 2-6e-7)
