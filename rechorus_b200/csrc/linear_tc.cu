@@ -238,7 +238,9 @@ k_linear_fwd_tc(const float* __restrict__ X, int ldx, const float* __restrict__ 
 //   iteration i:  wait(raw tile i landed) ; wait(MMA i-1 done: hi/lo free) ; split ; MMA i -> acc[i&1] ; refill ring with
 //                 tile i+NST ; epilogue i-1 from acc[(i-1)&1]
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TP_THREADS = 256;
+// 16 warps: with 8, each scheduler holds 2 warps and the kernel is bound by per-warp instruction latency (ncu: 20 % issue
+// slots, stalls spread over the split / epilogue chains) rather than by HBM, the tensor pipe or the ring depth
+constexpr int TP_THREADS = 512;
 
 __device__ __forceinline__ void tp_cp16(void* sdst, const void* gsrc, bool valid) {
     const uint32_t sa = tc_smem_u32(sdst);
@@ -246,25 +248,33 @@ __device__ __forceinline__ void tp_cp16(void* sdst, const void* gsrc, bool valid
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(nbytes) : "memory");
 }
 
-template <int KS, bool MASK>
+template <int KS, bool MASK, bool DB>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 k_linear_tc_pipe(const float* __restrict__ X, int ldx, const float* __restrict__ amask, const float* __restrict__ W,
                  const float* __restrict__ bias, float* __restrict__ Y, int ldy, int M, int N, int relu, int acc_cols,
-                 int nprod) {
+                 int nprod, int ko, int ystage_lg) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mma_bar[2];
     __shared__ uint32_t tmem_base_sh;
     constexpr int K = KS * 32;
-    constexpr int NST = MASK ? 2 : 3;                        // ring depth (a masked tile is two raw tiles)
+    // DB: two hi/lo operand buffers -- the split of tile i+1 runs while the MMAs of tile i execute (the tensor pipe, at
+    // ~2 cycles per accumulator column per 32-byte K chunk for kind::tf32, is the longest stage of a tile); the ring is then
+    // two tiles deep to stay inside 227 KB.  The masked form keeps one buffer (its ring stages are two raw tiles each).
+    constexpr int NST = (MASK || DB) ? 2 : 3;                // ring depth
     constexpr int CH = TC_M * K / 4;                         // 16-byte chunks per raw tile
     constexpr int CPT = CH / TP_THREADS;                     // chunks per thread
     const size_t a_slab = (size_t)TC_M * 128, b_slab = (size_t)N * 128, raw_tile = (size_t)TC_M * K * 4;
     char* A_hi = reinterpret_cast<char*>(smem_raw) + ((1024u - (tc_smem_u32(smem_raw) & 1023u)) & 1023u);
-    char* A_lo = A_hi + KS * a_slab;
-    char* B_hi = A_lo + KS * a_slab;
+    constexpr int NBUF = DB ? 2 : 1;
+    const size_t ab_bytes = 2 * KS * a_slab;                 // one operand buffer: A_hi slabs, then A_lo slabs
+    char* B_hi = A_hi + NBUF * ab_bytes;
     char* B_lo = B_hi + KS * b_slab;
     char* ring = B_lo + KS * b_slab;                         // NST x (raw X tile [, raw mask tile])
     const size_t stage_bytes = raw_tile * (MASK ? 2 : 1);
+    // output staging tile [128][N] (ystage_lg >= 0: N / 4 = 2^ystage_lg chunks per row, chunk index XOR (row & (N/4 - 1))):
+    // the accumulator comes out of TMEM one ROW per lane, and 16-byte stores at a 4N-byte lane stride cost a third of the
+    // kernel (knock-out measurement); through this tile the global stores are full rows
+    char* ystage = ring + NST * stage_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == 0) {
@@ -281,6 +291,7 @@ k_linear_tc_pipe(const float* __restrict__ X, int ldx, const float* __restrict__
     const int ntiles = (M + TC_M - 1) / TC_M;
     // ring prologue: tiles 0 .. NST-1 of this CTA
     auto issue_tile = [&](int tile, int stage) {
+        if (ko & 8) return;                                  // (diagnostic knock-outs, B2R_TC_KO: 1 MMA, 2 stores, 4 split, 8 loads)
         char* dst = ring + (size_t)stage * stage_bytes;
         const int m0 = tile * TC_M;
 #pragma unroll
@@ -311,22 +322,44 @@ k_linear_tc_pipe(const float* __restrict__ X, int ldx, const float* __restrict__
     const uint32_t tmem = tmem_base_sh;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
-    // epilogue of one finished tile: warp w reads TMEM lanes [32 (w & 3), +32) and the 16-column chunks of parity (w >> 2)
+    // epilogue of one finished tile: warp w reads TMEM lanes [32 (w & 3), +32) and the 16-column chunks (w >> 2), (w >> 2) + 4, ...
     auto epilogue = [&](int tile, uint32_t acc_base) {
-        const int row = tile * TC_M + (warp & 3) * 32 + lane;
-        for (int c0 = (warp >> 2) * 16; c0 < N; c0 += 32) {
+        const int row_l = (warp & 3) * 32 + lane;
+        const int row = tile * TC_M + row_l;
+        const int ncm = (1 << (ystage_lg < 0 ? 0 : ystage_lg)) - 1;
+        for (int c0 = (warp >> 2) * 16; c0 < N; c0 += 16 * (TP_THREADS / 128)) {
             float y16[16];
             tc_ld16(acc_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, y16);
-            if (row < M) {
+            if ((row < M || ystage_lg >= 0) && !(ko & 2)) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float y = y16[i] + (bias != nullptr ? __ldg(bias + c0 + i) : 0.f);
                     if (relu) y = fmaxf(y, 0.f);
                     y16[i] = y;
                 }
-                float* dst = Y + (size_t)row * ldy + c0;
+                if (ystage_lg >= 0) {
+                    char* srow = ystage + ((size_t)row_l << (ystage_lg + 4));
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(y16[i], y16[i + 1], y16[i + 2], y16[i + 3]);
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(srow + ((((c0 >> 2) + i) ^ (row_l & ncm)) << 4)) =
+                            make_float4(y16[4 * i], y16[4 * i + 1], y16[4 * i + 2], y16[4 * i + 3]);
+                } else {
+                    float* dst = Y + (size_t)row * ldy + c0;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(y16[i], y16[i + 1], y16[i + 2], y16[i + 3]);
+                }
+            }
+        }
+        if (ystage_lg >= 0) {
+            __syncthreads();                                  // (the epilogue is called by all threads, uniformly)
+            if (!(ko & 2)) {
+                const int m0 = tile * TC_M;
+                for (int e = tid; e < (TC_M << ystage_lg); e += TP_THREADS) {
+                    const int r = e >> ystage_lg, c = e & ncm;
+                    if (m0 + r < M)
+                        *reinterpret_cast<float4*>(Y + (size_t)(m0 + r) * ldy + c * 4) =
+                            *reinterpret_cast<const float4*>(ystage + ((size_t)r << (ystage_lg + 4)) + ((c ^ (r & ncm)) << 4));
+                }
             }
         }
     };
@@ -334,10 +367,14 @@ k_linear_tc_pipe(const float* __restrict__ X, int ldx, const float* __restrict__
     int it = 0, prev_tile = -1;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int stage = it % NST;
+        char* Ah = A_hi + (DB ? (size_t)(it & 1) * ab_bytes : 0);
+        char* Al = Ah + KS * a_slab;
         asm volatile("cp.async.wait_group %0;\n" ::"n"(NST - 1) : "memory");       // this thread's copies of tile `it` landed
-        if (it > 0) tc_mbar_wait(&mma_bar[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 done: hi/lo free
+        // single buffer: the MMAs of tile it-1 must have read hi/lo before the split overwrites them.  Double buffer: buffer
+        // it&1 was last read by the MMAs of tile it-2, whose completion every thread observed before its epilogue ran
+        if (!DB && it > 0) tc_mbar_wait(&mma_bar[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
         __syncthreads();                                                            // everyone's copies landed
-        {
+        if (!(ko & 4)) {
             const char* raw = ring + (size_t)stage * stage_bytes;
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
@@ -352,7 +389,7 @@ k_linear_tc_pipe(const float* __restrict__ X, int ldx, const float* __restrict__
                     v.w = mk.w > 0.f ? v.w : 0.f;
                 }
                 const int s_ = c / 8;
-                tc_store_split(A_hi + s_ * a_slab, A_lo + s_ * a_slab, r, c % 8, v);
+                tc_store_split(Ah + s_ * a_slab, Al + s_ * a_slab, r, c % 8, v);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -363,8 +400,8 @@ k_linear_tc_pipe(const float* __restrict__ X, int ldx, const float* __restrict__
             const uint32_t acc_base = tmem + (uint32_t)((it & 1) * acc_cols);
             uint32_t acc = 0;
 #pragma unroll 1
-            for (int prod = 0; prod < nprod; ++prod) {
-                const char* Ab = (prod < 2) ? A_hi : A_lo;
+            for (int prod = 0; prod < ((ko & 1) ? 0 : nprod); ++prod) {
+                const char* Ab = (prod < 2) ? Ah : Al;
                 const char* Bb = (prod & 1) ? B_lo : B_hi;
                 for (int s_ = 0; s_ < KS; ++s_) {
 #pragma unroll
@@ -384,6 +421,7 @@ k_linear_tc_pipe(const float* __restrict__ X, int ldx, const float* __restrict__
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
         if (it > 0) {
+            if (DB) tc_mbar_wait(&mma_bar[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));   // MMAs of tile it-1 (ran under this split)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             epilogue(prev_tile, tmem + (uint32_t)(((it - 1) & 1) * acc_cols));
         }
@@ -425,21 +463,36 @@ extern "C" int b2r_linear_tc(const float* X, int ldx, const float* x_mask, const
     static const bool use_pipe = !(getenv("B2R_TC_PIPE") && atoi(getenv("B2R_TC_PIPE")) == 0);
     static const int nprod = (getenv("B2R_TC_PRODS") && atoi(getenv("B2R_TC_PRODS")) == 4) ? 4 : 3;
     if (use_pipe && KS <= 2) {
-        const int nst = x_mask ? 2 : 3;
+        // B2R_TC_DB=1: double operand buffers (measured: no gain -- the tile time is set by the epilogue stores and the per-tile
+        // synchronisation, not by split + MMA); B2R_TC_STG=0: direct (row-strided) epilogue stores
+        static const bool want_db = getenv("B2R_TC_DB") && atoi(getenv("B2R_TC_DB")) == 1;
+        static const bool want_stg = !(getenv("B2R_TC_STG") && atoi(getenv("B2R_TC_STG")) == 0);
+        static const int ko = getenv("B2R_TC_KO") ? atoi(getenv("B2R_TC_KO")) : 0;     // diagnostic: wrong results by design
         const size_t raw_tile = (size_t)TC_M * K * 4;
-        const size_t psmem = (size_t)2 * KS * TC_M * 128 + (size_t)2 * KS * N * 128 + nst * raw_tile * (x_mask ? 2 : 1) + 1024;
-        if (psmem <= 227 * 1024 && 2 * cols <= 512) {
+        const size_t ab = (size_t)2 * KS * TC_M * 128, wb = (size_t)2 * KS * N * 128;
+        const size_t lim = 227 * 1024 - 64;
+        const size_t smem_db = 2 * ab + wb + 2 * raw_tile + 1024;
+        const bool db = want_db && !x_mask && smem_db <= lim;
+        const int nst = (x_mask || db) ? 2 : 3;
+        size_t psmem = db ? smem_db : ab + wb + nst * raw_tile * (x_mask ? 2 : 1) + 1024;
+        int ystage_lg = -1;
+        if (want_stg && (N == 16 || N == 32 || N == 64 || N == 128) && ldy % 4 == 0 &&
+            psmem + (size_t)TC_M * N * 4 <= lim) {
+            ystage_lg = N == 16 ? 2 : N == 32 ? 3 : N == 64 ? 4 : 5;
+            psmem += (size_t)TC_M * N * 4;
+        }
+        if (psmem <= lim && 2 * cols <= 512) {
             const int ntiles = (int)((M + TC_M - 1) / TC_M);
             int grid = sm_count();
             if (grid > ntiles) grid = ntiles;
-#define B2R_TP(KSV, MK)                                                                                       \
+#define B2R_TP(KSV, MK, DBV)                                                                                  \
     do {                                                                                                      \
-        B2R_CUDA_OK(cudaFuncSetAttribute(k_linear_tc_pipe<KSV, MK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
-        k_linear_tc_pipe<KSV, MK><<<grid, TP_THREADS, psmem, as_stream(stream)>>>(X, ldx, x_mask, W, bias, Y, ldy, (int)M, N, \
-                                                                                 relu, cols, nprod);         \
+        B2R_CUDA_OK(cudaFuncSetAttribute(k_linear_tc_pipe<KSV, MK, DBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
+        k_linear_tc_pipe<KSV, MK, DBV><<<grid, TP_THREADS, psmem, as_stream(stream)>>>(X, ldx, x_mask, W, bias, Y, ldy, (int)M, N, \
+                                                                                      relu, cols, nprod, ko, ystage_lg); \
     } while (0)
-            if (KS == 1) { if (x_mask) B2R_TP(1, true); else B2R_TP(1, false); }
-            else         { if (x_mask) B2R_TP(2, true); else B2R_TP(2, false); }
+            if (KS == 1) { if (x_mask) B2R_TP(1, true, false); else if (db) B2R_TP(1, false, true); else B2R_TP(1, false, false); }
+            else         { if (x_mask) B2R_TP(2, true, false); else if (db) B2R_TP(2, false, true); else B2R_TP(2, false, false); }
 #undef B2R_TP
             B2R_LAUNCH_OK("k_linear_tc_pipe");
             return 0;

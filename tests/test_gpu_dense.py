@@ -50,7 +50,7 @@ def test_linear_on_strided_input_columns():
     _close(y, F.linear(big[:, 64:], W))
 
 
-@pytest.mark.parametrize("rows,d", [(5, 64), (1000, 64), (77, 32), (300, 128)])
+@pytest.mark.parametrize("rows,d", [(5, 64), (1000, 64), (77, 32), (300, 128), (4099, 64), (10, 48)])
 def test_add_layernorm_forward_backward(rows, d):
     from rechorus_b200 import ops
     g = torch.Generator().manual_seed(rows + d)

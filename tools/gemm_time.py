@@ -34,6 +34,6 @@ for flag in (False, True):
     ops._TC_DW = flag
     print("dW   tc=%%s %%.1f us" %% (flag, t(lambda: ops.linear_bwd(dy, x, W, None, False, True, True))))
 ''' % ROOT
-for env in ({}, {"B2R_TC_CTAS": "2"}, {"B2R_TC_CTAS": "1"}, {"B2R_TC_PRODS": "4"}):
+for env in ({}, {"B2R_TC_STG": "0", "B2R_DW_SLB": "1"}):
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     print(env, "\n" + r.stdout.strip(), r.stderr.strip()[-800:])

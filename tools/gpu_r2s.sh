@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python tools/tc_check.py 2>&1 | tail -13 | cut -c1-200 | tee gpurun_out/r2x_tc_check.txt
+timeout 300 python tools/tc_dw_check.py 2>&1 | tail -8 | cut -c1-220 | tee gpurun_out/r2x_tc_dw_check.txt
+timeout 300 python tools/gemm_time.py 2>&1 | tee gpurun_out/r2x_gemm_time.txt
+timeout 300 python -m pytest tests/test_gpu_dense.py tests/test_gpu_models.py -q -x > gpurun_out/r2x_pytest.log 2>&1; echo "pytest rc=$? $(tail -1 gpurun_out/r2x_pytest.log)"
+grep -E "^FAILED|^ERROR|^E  " gpurun_out/r2x_pytest.log | head -20
+for W in c4; do
+timeout 600 python bench.py --workload $W --steps 20 --warmup 3 --no_cpu_baseline 2>gpurun_out/r2x_$W.err | tail -1 > gpurun_out/r2x_$W.json
+python -c "
+import json; d=json.load(open('gpurun_out/r2x_$W.json')); print('$W graphed ms %.4f eager %.4f e2e %.4f loss %s %s'%(d['ms_per_step'], d['eager_ms_per_step'], d['e2e']['ms_per_step'], d['final_loss'], d.get('graph_error')))"
+done
