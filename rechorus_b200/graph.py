@@ -35,9 +35,10 @@ class GraphedStep:
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        self.warmup_losses = []
         with torch.cuda.stream(side):               # eager warm-up steps (real steps: they train) off the default stream
             for _ in range(max(1, warmup)):
-                self._step()
+                self.warmup_losses.append(self._step().clone())
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()

@@ -70,7 +70,8 @@ class _KernelModelMixin:
                 from .optim import RowSparseOptimizer
                 a = self.__dict__.get("_b2r_args")
                 opt = RowSparseOptimizer(self, getattr(a, "optimizer", "Adam"), lr=getattr(a, "lr", 1e-3),
-                                         l2=getattr(a, "l2", 0.0))
+                                         l2=getattr(a, "l2", 0.0), exact_dense=bool(getattr(a, "exact_adam", 0)),
+                                         device_clock=bool(getattr(a, "graph_step", 0)))
                 self.__dict__["_b2r_optimizer"] = opt
         return opt
 

@@ -69,6 +69,10 @@ class BaseRunner:
         parser.add_argument("--fused_step", type=int, default=0,
                             help="1 (with --fused_optimizer 1): models that offer train_step run every training step "
                                  "as one C call (forward, loss, backward, optimizer; next batch's plan prefetched)")
+        parser.add_argument("--graph_step", type=int, default=0,
+                            help="1 (with --fused_optimizer 1): capture the loop body of fit (zero_grad, forward, loss, "
+                                 "backward, optimizer.step) once in a CUDA graph and replay it per full-size batch "
+                                 "(rechorus_b200.graph.GraphedStep); the ragged last batch runs eagerly")
         parser.add_argument("--exact_adam", type=int, default=0,
                             help="1 (with --fused_optimizer 1, Adam): row-sparse cost, dense torch.optim.Adam results "
                                  "(rows are advanced through their skipped steps)")
@@ -118,6 +122,10 @@ class BaseRunner:
         self.device_metrics = getattr(args, "device_metrics", 0)
         self.fused_step = getattr(args, "fused_step", 0)
         self.exact_adam = getattr(args, "exact_adam", 0)
+        self.graph_step = getattr(args, "graph_step", 0)
+        if self.graph_step and (self.exact_adam or not self.fused_optimizer):
+            raise ValueError("--graph_step 1 needs --fused_optimizer 1 and is not available with --exact_adam 1 "
+                             "(the exact mode keeps per-step host bookkeeping)")
         self.device_sampler = getattr(args, "device_sampler", 0)
         self.device_batches = getattr(args, "device_batches", 0)
         self.topk = [int(x) for x in args.topk.split(",")]
@@ -142,7 +150,7 @@ class BaseRunner:
         if self.fused_optimizer:
             model.set_table_mode("fused")
             return RowSparseOptimizer(model, self.optimizer_name, lr=self.learning_rate, l2=self.l2,
-                                      exact_dense=bool(self.exact_adam))
+                                      exact_dense=bool(self.exact_adam), device_clock=bool(self.graph_step))
         cls = getattr(torch.optim, self.optimizer_name)       # helpers/BaseRunner.py:112
         return cls(model.customize_parameters(), lr=self.learning_rate, weight_decay=self.l2)
 
@@ -210,6 +218,39 @@ class BaseRunner:
         finally:
             ops.bprmf_step_reset()
         out = float(np.mean(torch.stack(losses).cpu().numpy())) if losses else float("nan")
+        _poll_ids(model)
+        return out
+
+    def _fit_graphed(self, dataset, epoch=-1) -> float:
+        """The same epoch with the loop body of helpers/BaseRunner.py:193-206 captured once in a CUDA graph
+        (rechorus_b200.graph.GraphedStep) and replayed for every batch of the captured shape: one launch per step instead of
+        ~70 (NeuMF) to ~150 (SASRec).  The first full-size batch trains through the capture's eager warm-up step; the ragged
+        last batch runs eagerly.  As in ``_fit_whole_steps`` the per-row candidate permutation of :189 is drawn (RNG stream in
+        step with the reference) but not applied: it is a no-op for candidates scored independently.  Models with dropout keep
+        the eager loop (``fit`` does not route them here)."""
+        from .graph import GraphedStep
+        model = dataset.model
+        dl = DataLoader(dataset, batch_size=self.batch_size, shuffle=True, num_workers=self.num_workers,
+                        collate_fn=dataset.collate_batch, pin_memory=bool(self.pin_memory))
+        losses = []
+        for batch in dl:
+            batch = batch_to_device(batch, model.device)
+            torch.rand(*batch["item_id"].shape)                       # BaseRunner.py:189's draw
+            gs = model.__dict__.get("_b2r_graphed_step")
+            if gs is None and batch["item_id"].shape[0] == self.batch_size:
+                gs = GraphedStep(model, batch, warmup=1)              # its warm-up step IS this batch's training step
+                model.__dict__["_b2r_graphed_step"] = gs
+                losses.append(gs.warmup_losses[0])
+            elif gs is not None and gs.matches(batch):
+                losses.append(gs(batch).clone())
+            else:
+                model.optimizer.zero_grad()
+                loss = model.loss(model(batch))
+                loss.backward()
+                model.optimizer.step()
+                losses.append(loss.detach())
+        model.optimizer.sync_clock()                                  # the host step counter follows the device clock
+        out = float(np.mean(torch.stack([l.reshape(()) for l in losses]).cpu().numpy())) if losses else float("nan")
         _poll_ids(model)
         return out
 
@@ -287,8 +328,9 @@ class BaseRunner:
     def fit(self, dataset, epoch=-1) -> float:
         """helpers/BaseRunner.py:174-208, step for step."""
         model = dataset.model
-        if model.optimizer is None:
-            model.optimizer = self._build_optimizer(model)
+        opt = model.optimizer
+        if opt is None or (self.graph_step and isinstance(opt, RowSparseOptimizer) and not opt._want_clock and opt.t == 0):
+            model.optimizer = self._build_optimizer(model)     # (a lazily built one without the device clock is replaced)
         if self.device_sampler and model.__dict__.get("_b2r_device_sampler") is None:
             corpus = dataset.corpus
             model.__dict__["_b2r_device_sampler"] = ops.DeviceNegativeSampler(
@@ -299,6 +341,8 @@ class BaseRunner:
         model.train()
         if self.fused_step and hasattr(model, "train_step") and isinstance(model.optimizer, RowSparseOptimizer):
             return self._fit_whole_steps(dataset, epoch)
+        if self.graph_step and isinstance(model.optimizer, RowSparseOptimizer) and not getattr(model, "dropout", 0):
+            return self._fit_graphed(dataset, epoch)
         losses = []
         dl = DataLoader(dataset, batch_size=self.batch_size, shuffle=True, num_workers=self.num_workers,
                         collate_fn=dataset.collate_batch, pin_memory=bool(self.pin_memory))

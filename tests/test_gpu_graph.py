@@ -90,3 +90,48 @@ def test_capture_after_eager_steps_on_the_default_stream():
     m.loss(m(feeds[0])).backward()
     m.optimizer.step()
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("model_name,extra", [("NeuMF", ["--emb_size", "32", "--layers", "[32]"]),
+                                              ("BPRMF", ["--emb_size", "64"])])
+def test_runner_graph_step_trains_like_the_eager_loop(model_name, extra):
+    """--graph_step 1: BaseRunner.fit replays the captured loop body for the full-size batches (the first one trains through
+    the capture's warm-up step, the ragged last one eagerly); two epochs must end where the eager loop ends (which also
+    applies the reference's candidate shuffle -- a no-op up to summation order)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import fit_corpus
+    from rechorus_b200 import plugin
+    from rechorus_b200.runner import BaseRunner
+    cls = getattr(plugin, model_name)
+
+    def run(graph):
+        p = argparse.ArgumentParser()
+        p = BaseRunner.parse_runner_args(p)
+        p = cls.parse_model_args(p)
+        a = p.parse_args(extra + ["--num_neg", "5", "--batch_size", "64", "--num_workers", "0", "--lr", "0.001", "--optimizer",
+                                  "Adam", "--table_mode", "fused", "--fused_optimizer", "1", "--graph_step", str(graph)])
+        a.device, a.model_path, a.log_file = torch.device("cuda", 0), "/tmp/_b2r_gs.pt", ""
+        corpus = fit_corpus.build()
+        torch.manual_seed(1)
+        import numpy as np
+        np.random.seed(1)
+        model = cls(a, corpus).to(a.device)
+        train = cls.Dataset(model, corpus, "train")
+        runner = BaseRunner(a)
+        ls = [runner.fit(train, epoch=e) for e in (1, 2)]
+        torch.cuda.synchronize()
+        return model, ls, runner
+
+    m0, l0, _ = run(0)
+    m1, l1, r1 = run(1)
+    assert "_b2r_graphed_step" in m1.__dict__ and m1.optimizer.t == m0.optimizer.t
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-4, (l0, l1)
+    # the two loops differ in summation order only (the eager one scores shuffled columns); Adam turns a 1e-10 difference
+    # of a gradient entry that is within a few orders of eps into a visible fraction of lr (DESIGN.md section 6), so the
+    # bulk is bounded tightly and the ill-conditioned tail by a few steps' worth of lr (measured: max 3e-4 at lr 1e-3)
+    for (k, pa), (_, pb) in zip(m0.named_parameters(), m1.named_parameters()):
+        d = (pa.detach() - pb.detach()).abs().flatten()
+        assert float(d.median()) <= 1e-6 and float(d.max()) <= 5e-3, (k, float(d.median()), float(d.max()))
