@@ -124,3 +124,14 @@ def test_metrics_from_histogram_equal_evaluate_method():
     import pytest
     with pytest.raises(ValueError):
         ops.metrics_from_histogram(hist, len(rank), [5], ["MRR"])
+
+
+def test_graph_step_flag_needs_the_fused_optimizer_and_excludes_exact_adam():
+    """--graph_step replays the loop body from a CUDA graph: it needs the RowSparseOptimizer's device-side clock (so
+    --fused_optimizer 1) and cannot keep the exact-Adam mode's per-step host bookkeeping"""
+    with pytest.raises(ValueError):
+        BaseRunner(_args(plugin.BPRMF, ["--graph_step", "1"]))
+    with pytest.raises(ValueError):
+        BaseRunner(_args(plugin.BPRMF, ["--graph_step", "1", "--fused_optimizer", "1", "--exact_adam", "1"]))
+    r = BaseRunner(_args(plugin.BPRMF, ["--graph_step", "1", "--fused_optimizer", "1"]))
+    assert r.graph_step == 1 and BaseRunner(_args(plugin.BPRMF, [])).graph_step == 0
